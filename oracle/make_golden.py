@@ -1,0 +1,57 @@
+"""TEST INFRASTRUCTURE ONLY -- freeze outputs of the REFERENCE's own functions.
+
+Run in the build container (needs /root/reference):
+
+    python -m oracle.make_golden            # writes tests/golden/<variant>.npz
+
+For each task variant a small seeded synthetic state (inputs included in the
+fixture, so it is self-contained) is pushed through the reference's
+`compute_*_reward` and `compute_*_observations` functions, cut unmodified out of
+/root/reference by `oracle/ref_extract.py`, composed exactly as the class
+wrappers do (`oracle/task_oracle.py`).  The GPU box has no /root/reference;
+there the fixtures are what pins both the oracle and the CUDA path.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from isaacgym_b200.config import CONFIGS  # noqa: E402
+from isaacgym_b200.synth import clone_state, make_state  # noqa: E402
+from oracle import ref_extract, task_oracle  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+NUM_ENVS = 96
+SEED = 20261018
+
+
+def main():
+    assert ref_extract.available(), "needs /root/reference"
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    ref = task_oracle.ReferenceImpl()
+    torch.set_num_threads(1)
+    for variant, cfg in CONFIGS.items():
+        st_in = make_state(cfg, NUM_ENVS, seed=SEED + cfg.variant_id)
+        st = clone_state(st_in)
+        if variant != "base":
+            st["progress_buf"] += 1                      # post_physics_step does this before compute_reward
+        with ref_extract.quiet():
+            task_oracle.compute_reward(cfg, st, ref)
+            obs = task_oracle.compute_observations(cfg, st, ref)
+        out = {"in__" + k: v.numpy() for k, v in st_in.items()}
+        out["out__obs_buf"] = obs.numpy()
+        out["out__rew_buf"] = st["rew_buf"].numpy()
+        out["out__reset_buf"] = st["reset_buf"].numpy()
+        for name in cfg.flag_names + cfg.counter_names:
+            out["out__" + name] = st[name].numpy()
+        path = os.path.join(GOLDEN_DIR, f"{variant}.npz")
+        np.savez_compressed(path, **out)
+        print(f"{variant}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), "
+              f"resets={int(st['reset_buf'].sum())}, mean reward={float(st['rew_buf'].mean()):.4f}")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,130 @@
+"""TEST INFRASTRUCTURE ONLY -- loader for the reference's OWN function source.
+
+Works only where `/root/reference` exists (the build container).  The task
+modules cannot be imported (they import `isaacgym`, `isaacgymenvs`, which are
+absent), so each top-level function is cut out of the reference file by AST
+position, written UNMODIFIED into a file-backed temporary module
+(`torch.jit.script` needs real source files) with the restated
+`torch_jit_utils` helpers in scope, and imported from there.  Nothing is copied
+into the repository: the temp modules live under a `tempfile` directory.
+
+Used by `oracle/make_golden.py` (fixture generation) and by the `not gpu`
+tests that pin `oracle/pingpong_oracle.py` against the reference.
+"""
+import ast
+import contextlib
+import importlib.util
+import os
+import sys
+import tempfile
+
+REFERENCE_ROOT = os.environ.get("PPK_REFERENCE_ROOT", "/root/reference")
+
+# alias -> file (SURVEY.md header table)
+FILES = {
+    "BASE": "tasks/humanoid_pingpong.py",
+    "A3": "tasks/humanoid_interos_edit_pingpong_only_3_actor.py",
+    "TILT": "tasks/humanoid_pingpong_3_actor_tilt.py",
+    "NES": "tasks/humanoid_pingpong_3_actor_tilt_no_earlystop.py",
+    "A4": "tasks/humanoid_pingpong_4_actor_tilt.py",
+    "ALIGN": "tasks/humanoid_pingpong_alignment.py",
+    "ADOF": "tasks/humanoid_pingpong_3_actor_all_dof.py",
+}
+
+_HEADER = (
+    "import math\n"
+    "import torch\n"
+    "from torch import Tensor\n"
+    "from typing import Tuple, Dict, List, Optional\n"
+    "from oracle.jit_utils_restated import *\n"
+)
+
+_tmpdir = None
+_cache = {}
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "tasks"))
+
+
+@contextlib.contextmanager
+def quiet():
+    """Silence fd 1: the reference reward functions print (TorchScript prints
+    bypass sys.stdout), e.g. TILT:1216-1217."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    try:
+        os.dup2(devnull, 1)
+        with contextlib.redirect_stdout(open(os.devnull, "w")):
+            yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+
+
+def _function_sources(alias):
+    path = os.path.join(REFERENCE_ROOT, FILES[alias])
+    text = open(path, encoding="utf-8").read()
+    lines = text.splitlines(keepends=True)
+    out = []
+    for node in ast.parse(text).body:
+        if isinstance(node, ast.FunctionDef):
+            first = min([node.lineno] + [d.lineno for d in node.decorator_list])
+            out.append((node.name, first, "".join(lines[first - 1:node.end_lineno])))
+    return out
+
+
+def load(alias, name, occurrence=0, extra_globals=None):
+    """Return reference function `name` of file `alias`.
+
+    `occurrence` selects among same-named top-level definitions (ALIGN defines
+    `compute_pingpong_reward` twice; #0 is the live one, ALIGN:1097).
+    Functions may reference other top-level functions of the same file
+    (ADOF reward -> compute_imitation_reward, compute_gradient_penalty); name
+    them in `extra_globals` as {name: callable}.
+    """
+    global _tmpdir
+    key = (alias, name, occurrence)
+    if key in _cache:
+        return _cache[key]
+    if not available():
+        raise RuntimeError(f"{REFERENCE_ROOT} is not present; the reference loader "
+                           "only works in the build container")
+    matches = [s for s in _function_sources(alias) if s[0] == name]
+    if occurrence >= len(matches):
+        raise KeyError(f"{alias}:{name}#{occurrence} not found")
+    _, lineno, src = matches[occurrence]
+    if _tmpdir is None:
+        _tmpdir = tempfile.mkdtemp(prefix="ppk_ref_")
+    modname = f"_ppkref_{alias}_{name}_{occurrence}"
+    fpath = os.path.join(_tmpdir, modname + ".py")
+    pre = ""
+    if extra_globals:
+        pre = "".join(f"{k} = __import__('oracle.ref_extract', fromlist=['x'])._EXTRA[{k!r}]\n"
+                      for k in extra_globals)
+        _EXTRA.update(extra_globals)
+    with open(fpath, "w", encoding="utf-8") as f:
+        f.write(_HEADER + pre + f"# cut from {FILES[alias]}:{lineno}\n" + src)
+    spec = importlib.util.spec_from_file_location(modname, fpath)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    with quiet():
+        spec.loader.exec_module(mod)
+    fn = getattr(mod, name)
+    _cache[key] = fn
+    return fn
+
+
+_EXTRA = {}
+
+
+def load_adof_reward():
+    """ADOF:1440 calls ADOF:1313 and ADOF:1245 by module-level name."""
+    imi = load("ADOF", "compute_imitation_reward")
+    grad = load("ADOF", "compute_gradient_penalty")
+    return load("ADOF", "compute_pingpong_reward_nv",
+                extra_globals={"compute_imitation_reward": imi,
+                               "compute_gradient_penalty": grad})
