@@ -1,0 +1,434 @@
+// Fused task step of the 27-DOF variant (humanoid_pingpong_3_actor_all_dof.py, ADOF).
+//
+// Per env the step consumes rows 0..39 of the rigid-body tensor (2080 contiguous bytes), rows
+// 0..27 of the initial (reference-pose) rigid-body tensor, 27 DOF states, their reference and the
+// DOF forces, and writes a 313-float observation row.  One warp owns a tile of 8 envs:
+//   stage    flat coalesced loads into the warp's shared-memory slice;
+//   phase B  one env per pass, lane = balance body (23) and lane = DOF (27): imitation diffs,
+//            the seven per-env reductions of compute_imitation_reward (ADOF:1313-1418) by warp
+//            shuffles, heading frames, imitation observation segments (ADOF:1891-1927);
+//   phase R  lane = env: compute_pingpong_reward_nv (ADOF:1440-1690) + compute_gradient_penalty
+//            (ADOF:1245-1301), flags, counters, time-out mask, predicated reset (ADOF:965-1028);
+//   phase P  lane = (env, body): the ten ping-pong bodies in the heading frame (ADOF:1849-1888);
+//   tail     dof / ball / reference-dof segments, lane = element.
+#pragma once
+#include "ppk_device.cuh"
+
+namespace ppk {
+
+constexpr int kAdofTile = 8;
+constexpr int kAdofWarps = 2;
+constexpr int kAdofD = 27;
+constexpr int kAdofJ = 10;       // ping-pong bodies
+constexpr int kAdofNB = 23;      // balance bodies
+constexpr int kAdofRbRows = 40;  // rows 0..39 staged from the live tensor
+constexpr int kAdofInitRows = 28;  // rows 0..27 staged from the reference pose
+constexpr int kAdofObs = 6 * kAdofJ + 2 * kAdofD + 7 + 6 * kAdofNB + 2 * kAdofD;   // 313
+
+struct AdofLayout {
+  static constexpr int kRbEnv = kAdofRbRows * kRow;      // 520
+  static constexpr int kInitEnv = kAdofInitRows * kRow;  // 364
+  static constexpr int kSRb = kRbEnv | 1;
+  static constexpr int kSInit = kInitEnv | 1;
+  static constexpr int kSRoot = 3 * kRow;                // 39
+  static constexpr int kSDof = (2 * kAdofD) | 1;         // 55
+  static constexpr int kSForce = kAdofD;                 // 27
+  static constexpr int kSHdr = 24;
+  static constexpr int kOffInit = kAdofTile * kSRb;
+  static constexpr int kOffRoot = kOffInit + kAdofTile * kSInit;
+  static constexpr int kOffDof = kOffRoot + kAdofTile * kSRoot;
+  static constexpr int kOffIDof = kOffDof + kAdofTile * kSDof;
+  static constexpr int kOffForce = kOffIDof + kAdofTile * kSDof;
+  static constexpr int kOffHdr = kOffForce + kAdofTile * kSForce;
+  static constexpr int kWarpFloats = kOffHdr + kAdofTile * kSHdr;
+};
+// hdr slots per env
+enum { H_RX = 0, H_RY, H_RZ, H_SZ, H_CW,            // ping-pong heading frame (body ids[0])
+       H_SUM_DP2, H_SUM_DV2, H_SUM_NORM,            // balance-body reductions
+       H_SUM_DQ22, H_SUM_DQ5, H_SUM_DQD22, H_POWER, // DOF reductions
+       H_BALL0, H_BALL1, H_BALL2, H_BALL3, H_BALL4, H_BALL5, H_BALL6 };
+
+template <int ITERS, int ENV_FLOATS, int S>
+__device__ __forceinline__ void stage_flat(float* dst, const float* g, int valid_floats, int lane) {
+  // the tile's slice is contiguous in global memory: float f of the slice -> dst[(f / ENV)*S + f % ENV]
+  constexpr int kBatch = ITERS > 48 ? 48 : ITERS;
+#pragma unroll 1
+  for (int it0 = 0; it0 < ITERS; it0 += kBatch) {
+    float v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      int f = (it0 + u) * 32 + lane;
+      v[u] = (it0 + u < ITERS && f < valid_floats) ? ld_stream(g + f) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      int f = (it0 + u) * 32 + lane;
+      int e = f / ENV_FLOATS, r = f - e * ENV_FLOATS;
+      if (it0 + u < ITERS && e < kAdofTile) dst[e * S + r] = v[u];
+    }
+  }
+}
+
+template <int ITERS, int ENV_FLOATS, int S>
+__device__ __forceinline__ void stage_rows(float* dst, const float* g, int env_stride, int nvalid, int lane) {
+  // ENV_FLOATS contiguous floats per env, envs env_stride floats apart
+  constexpr int kBatch = ITERS > 48 ? 48 : ITERS;
+#pragma unroll 1
+  for (int it0 = 0; it0 < ITERS; it0 += kBatch) {
+    float v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      int f = (it0 + u) * 32 + lane;
+      int e = f / ENV_FLOATS, r = f - e * ENV_FLOATS;
+      v[u] = (it0 + u < ITERS && e < nvalid) ? ld_stream(g + (size_t)e * env_stride + r) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      int f = (it0 + u) * 32 + lane;
+      int e = f / ENV_FLOATS, r = f - e * ENV_FLOATS;
+      if (it0 + u < ITERS && e < kAdofTile) dst[e * S + r] = v[u];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kAdofWarps * 32)
+adof_step_kernel(const __grid_constant__ KArgs k) {
+  using L = AdofLayout;
+  extern __shared__ float smem[];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long tile = (long long)blockIdx.x * kAdofWarps + warp;
+  const long long env0 = tile * kAdofTile;
+  if (env0 >= k.n) return;
+  const int nvalid = (int)min((long long)kAdofTile, k.n - env0);
+  constexpr int D = kAdofD, J = kAdofJ, NB = kAdofNB, T = kAdofTile;
+
+  float* rb_s = smem + (size_t)warp * L::kWarpFloats;
+  float* init_s = rb_s + L::kOffInit;
+  float* root_s = rb_s + L::kOffRoot;
+  float* dof_s = rb_s + L::kOffDof;
+  float* idof_s = rb_s + L::kOffIDof;
+  float* force_s = rb_s + L::kOffForce;
+  float* hdr_s = rb_s + L::kOffHdr;
+  const int phases = k.phases;
+
+  // ---- stage -------------------------------------------------------------------------------
+  stage_flat<(T * 39 + 31) / 32, 39, L::kSRoot>(root_s, k.root + (size_t)env0 * 39, nvalid * 39, lane);
+  stage_flat<(T * 2 * D + 31) / 32, 2 * D, L::kSDof>(dof_s, k.dof + (size_t)env0 * 2 * D, nvalid * 2 * D, lane);
+  stage_flat<(T * 2 * D + 31) / 32, 2 * D, L::kSDof>(idof_s, k.init_dof + (size_t)env0 * 2 * D, nvalid * 2 * D, lane);
+  stage_flat<(T * D + 31) / 32, D, L::kSForce>(force_s, k.force + (size_t)env0 * D, nvalid * D, lane);
+  stage_rows<(T * L::kRbEnv + 31) / 32, L::kRbEnv, L::kSRb>(rb_s, k.rb + (size_t)env0 * k.B * kRow, k.B * kRow, nvalid, lane);
+  stage_rows<(T * L::kInitEnv + 31) / 32, L::kInitEnv, L::kSInit>(init_s, k.init_rb + (size_t)env0 * k.B * kRow, k.B * kRow, nvalid, lane);
+  __syncwarp();
+
+  float* g_obs = k.obs + (size_t)env0 * kAdofObs;
+  const int bal_id = (lane < NB) ? k.bal_ids[lane] : k.bal_ids[0];
+  const int bal_root = k.bal_ids[0];
+  const int pp_root = k.ids[0][0];
+
+  // ---- phase B: one env per pass; lane = balance body and lane = DOF -----------------------------
+#pragma unroll 1
+  for (int e = 0; e < T; ++e) {
+    const float* rb_e = rb_s + e * L::kSRb;
+    const float* in_e = init_s + e * L::kSInit;
+    const float* cur = rb_e + bal_id * kRow;
+    const float* ref = in_e + bal_id * kRow;
+    const bool body_on = lane < NB;
+    // imitation diffs: ref - cur (ADOF:1345,1349 / ADOF:1908-1909)
+    float dpx = ref[0] - cur[0], dpy = ref[1] - cur[1], dpz = ref[2] - cur[2];
+    float dvx = ref[7] - cur[7], dvy = ref[8] - cur[8], dvz = ref[9] - cur[9];
+    // has_fallen uses cur - ref (ADOF:1412)
+    float nx = cur[0] - ref[0], ny = cur[1] - ref[1], nz = cur[2] - ref[2];
+    float s_dp2 = body_on ? (dpx * dpx + dpy * dpy + dpz * dpz) / 3.0f : 0.0f;
+    float s_dv2 = body_on ? (dvx * dvx + dvy * dvy + dvz * dvz) / 3.0f : 0.0f;
+    float s_nrm = body_on ? sqrtf(nx * nx + ny * ny + nz * nz) : 0.0f;
+    // DOF terms, lane = DOF index
+    const bool dof_on = lane < D;
+    const int dl = dof_on ? lane : 0;
+    float q = dof_s[e * L::kSDof + 2 * dl], qd = dof_s[e * L::kSDof + 2 * dl + 1];
+    float rq = idof_s[e * L::kSDof + 2 * dl], rqd = idof_s[e * L::kSDof + 2 * dl + 1];
+    float dq = rq - q, dqd = rqd - qd;
+    float s_dq22 = (dof_on && lane < 22) ? dq * dq : 0.0f;
+    float s_dq5 = (dof_on && lane >= 22) ? dq * dq : 0.0f;
+    float s_dqd22 = (dof_on && lane < 22) ? dqd * dqd : 0.0f;
+    float s_pow = dof_on ? fabsf(force_s[e * L::kSForce + dl] * qd) : 0.0f;
+    s_dp2 = warp_sum(s_dp2); s_dv2 = warp_sum(s_dv2); s_nrm = warp_sum(s_nrm);
+    s_dq22 = warp_sum(s_dq22); s_dq5 = warp_sum(s_dq5); s_dqd22 = warp_sum(s_dqd22); s_pow = warp_sum(s_pow);
+    // heading frames: ping-pong root body and balance root body (both row 0 in the shipped config)
+    const float* r0 = rb_e + pp_root * kRow;
+    Heading hq_pp = heading_quat_inv(r0[3], r0[4], r0[5], r0[6]);
+    const float* b0 = rb_e + bal_root * kRow;
+    Heading hq_bal = (bal_root == pp_root) ? hq_pp : heading_quat_inv(b0[3], b0[4], b0[5], b0[6]);
+    if (lane == 0) {
+      float* hd = hdr_s + e * L::kSHdr;
+      hd[H_RX] = r0[0]; hd[H_RY] = r0[1]; hd[H_RZ] = r0[2]; hd[H_SZ] = hq_pp.sz; hd[H_CW] = hq_pp.cw;
+      hd[H_SUM_DP2] = s_dp2; hd[H_SUM_DV2] = s_dv2; hd[H_SUM_NORM] = s_nrm;
+      hd[H_SUM_DQ22] = s_dq22; hd[H_SUM_DQ5] = s_dq5; hd[H_SUM_DQD22] = s_dqd22; hd[H_POWER] = s_pow;
+    }
+    if ((phases & PPK_PHASE_OBS) && e < nvalid) {
+      // imitation observation segments [121,190) = 10*R(dP), [190,259) = R(dV)
+      float lp[3], lv[3];
+      rotate_heading(hq_bal, dpx, dpy, dpz, lp[0], lp[1], lp[2]);
+      rotate_heading(hq_bal, dvx, dvy, dvz, lv[0], lv[1], lv[2]);
+      lp[0] *= 10.0f; lp[1] *= 10.0f; lp[2] *= 10.0f;
+      float* orow = g_obs + (size_t)e * kAdofObs + (6 * J + 2 * D + 7);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int o = (body_on ? lane : 0) + i * NB;
+        const int src = o / 3, comp = o - src * 3;
+        float x = __shfl_sync(full, lp[0], src), y = __shfl_sync(full, lp[1], src), z = __shfl_sync(full, lp[2], src);
+        float pv = comp == 0 ? x : (comp == 1 ? y : z);
+        x = __shfl_sync(full, lv[0], src); y = __shfl_sync(full, lv[1], src); z = __shfl_sync(full, lv[2], src);
+        float vv = comp == 0 ? x : (comp == 1 ? y : z);
+        if (body_on) { st_stream(orow + o, pv); st_stream(orow + 3 * NB + o, vv); }
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- phase R: lane = env ---------------------------------------------------------------------
+  const bool lane_env = lane < nvalid;
+  const int le = (lane < T) ? lane : 0;
+  const long long env = env0 + le;
+  float* hd = hdr_s + le * L::kSHdr;
+  const float* my_root = root_s + le * L::kSRoot;
+  const float* ball = my_root + k.ball * kRow;
+  float bx = ball[0], by = ball[1], bz = ball[2], bvx = ball[7], bvy = ball[8], bvz = ball[9];
+  long long prog = 0, reset_prev = 0;
+  if (lane_env) {
+    prog = k.progress[env];
+    if (!(phases & PPK_PHASE_REWARD)) reset_prev = k.reset[env];
+  }
+  long long p_new = prog + ((phases & PPK_PHASE_PROGRESS) ? 1 : 0);
+  bool is_reset = reset_prev != 0;
+  float reward = 0.0f;
+  bool f_pcc = false, f_htc = false, f_dpc = false, f_hdc = false;
+  bool c_closer = false, c_hitp = false, c_net = false, c_table = false, c_fall = false;
+
+  if (phases & PPK_PHASE_REWARD) {
+    float pre_vx = 0.0f;
+    if (lane_env) {
+      pre_vx = ld_stream(k.pre + (size_t)env * k.pre_stride + k.pre_vx);
+      f_pcc = k.flags[0][env] != 0; f_htc = k.flags[1][env] != 0; f_dpc = k.flags[2][env] != 0; f_hdc = k.flags[3][env] != 0;
+      c_closer = k.flags[4][env] != 0; c_hitp = k.flags[5][env] != 0; c_net = k.flags[6][env] != 0;
+      c_table = k.flags[7][env] != 0; c_fall = k.flags[8][env] != 0;
+    }
+    // compute_imitation_reward, is_g1 branch (ADOF:1330-1418)
+    float r_body_pos = expf(-50.0f * (hd[H_SUM_DP2] / (float)NB));
+    float r_body_vel = expf(-4.0f * (hd[H_SUM_DV2] / (float)NB));
+    float first22 = 10.0f * expf(-2500.0f * (hd[H_SUM_DQ22] / 22.0f));
+    float last5 = 0.2f * expf(-5.0f * (hd[H_SUM_DQ5] / 5.0f));
+    float r_dof_vel = expf(-0.05f * (hd[H_SUM_DQD22] / 22.0f));
+    float ref_reward = (((first22 + last5) + 0.2f * r_dof_vel) + 0.4f * r_body_pos) + 0.2f * r_body_vel;
+    bool has_fallen = (hd[H_SUM_NORM] / (float)NB) > k.term_dist;
+    if (has_fallen) ref_reward = 1.0f * -50.0f;
+    c_fall = c_fall || has_fallen;
+
+    const float* pd = rb_s + le * L::kSRb + k.paddle_body[0] * kRow;
+    float px = pd[0], py = pd[1], pz = pd[2];
+    float pelvis_z = rb_s[le * L::kSRb + k.pelvis_body * kRow + 2];
+    float hx = my_root[k.hum[0] * kRow];
+    bool x_close = fabsf(bx - px) < 0.2f;
+    bool first_close = x_close && !f_pcc;
+    float dy = by - py, dz = bz - pz;
+    float yz = sqrtf(dy * dy + dz * dz);
+    bool in_circle = yz < 0.15f;
+    float pos_reward = (first_close && !f_hdc) ? (in_circle ? k.hit_paddle : k.miss_coef * yz) : 0.0f;
+    c_closer = c_closer || (first_close && in_circle);
+    bool hit = (pre_vx < 0.0f) && (bvx > 1.5f);
+    c_hitp = c_hitp || hit;
+    float vel_reward = (hit && !f_pcc && !f_hdc) ? k.alpha * fabsf(bvx) : 0.0f;
+    f_pcc = f_pcc || x_close;
+    float time_penalty = ((bx > hx) && (bvx < 0.0f)) ? -0.01f * (float)p_new : 0.0f;
+    // compute_gradient_penalty (ADOF:1245-1301)
+    bool z_in = (bz >= 0.82f) && (bz <= 0.83f) && (bvx > 0.0f);
+    float ddx = bx - 2.5f, ddy = by - 0.0f;
+    float dist = sqrtf(ddx * ddx + ddy * ddy);
+    bool in_range = (bx >= 1.9f) && (bx <= 3.1f) && (by >= -0.6f) && (by <= 0.6f);
+    c_table = c_table || (z_in && in_range);
+    float table = (z_in && !f_htc && !f_hdc) ? (in_range ? k.hit_table : k.not_hit * dist) : 0.0f;
+    f_htc = f_htc || z_in;
+    // net (ADOF:1619-1650)
+    bool over_net = (bx > 1.72f) && (bx < 1.78f) && (bvx > 0.0f);
+    bool suitable = (bz > 0.96f) && (bz < 1.25f);
+    float over_h = !suitable ? ((bz > 1.25f) ? (bz - 1.25f) : (0.96f - bz)) : 0.0f;
+    float net = (over_net && !f_hdc) ? (suitable ? k.cross_net : -400.0f * over_h) : 0.0f;
+    c_net = c_net || (net > 0.0f);
+    float power_reward = (-k.power_coef) * hd[H_POWER];
+    bool low = bz < 0.78f;
+    float die_pen = (low && !f_dpc && !f_hdc) ? k.die_penalty : 0.0f;
+    f_dpc = f_dpc || low;
+    f_hdc = f_hdc || (pelvis_z < 0.97f);
+    reward = 0.0f + (((((((pos_reward + power_reward) + vel_reward) + table) + net) + die_pen) + time_penalty) + ref_reward);
+    is_reset = p_new >= k.max_len - 1;          // die stays 0 (ADOF:1688)
+    if (lane_env) {
+      k.rew[env] = reward;
+      k.reset[env] = is_reset ? 1 : 0;
+    }
+  }
+
+  if (phases & PPK_PHASE_STATS) {
+    double v[PPK_NUM_STATS];
+    v[PPK_STAT_REWARD] = lane_env ? (double)reward : 0.0;
+    v[PPK_STAT_PROGRESS] = lane_env ? (double)p_new : 0.0;
+    v[PPK_STAT_RESETS] = (lane_env && is_reset) ? 1.0 : 0.0;
+    v[PPK_STAT_FALL_DOWN] = (lane_env && c_fall) ? 1.0 : 0.0;
+    v[PPK_STAT_CLOSER] = (lane_env && c_closer) ? 1.0 : 0.0;
+    v[PPK_STAT_HIT_PADDLE] = (lane_env && c_hitp) ? 1.0 : 0.0;
+    v[PPK_STAT_CROSS_NET] = (lane_env && c_net) ? 1.0 : 0.0;
+    v[PPK_STAT_HIT_TABLE] = (lane_env && c_table) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 0; i < PPK_NUM_STATS; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0) {
+      double* slot = k.stats + (size_t)(tile % PPK_STATS_SLOTS) * PPK_NUM_STATS;
+#pragma unroll
+      for (int i = 0; i < PPK_NUM_STATS; ++i) atomicAdd(slot + i, v[i]);
+    }
+  }
+
+  // ---- predicated reset (ADOF:965-1028) ----------------------------------------------------------
+  const bool do_reset = (phases & PPK_PHASE_RESET) && is_reset && lane_env;
+  if (do_reset) {
+    const float* ir = k.init_root + (size_t)env * 39;
+    float* gr = k.root + (size_t)env * 39;
+    const float* rv = k.reset_vel + (size_t)env * 3;
+    const float* ryz = k.reset_yz + (size_t)env * 2;
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int c = 0; c < 7; ++c) gr[a * kRow + c] = ir[a * kRow + c];
+#pragma unroll
+      for (int c = 7; c < kRow; ++c) gr[a * kRow + c] = 0.0f;
+    }
+    bx = ir[k.ball * kRow + 0]; by = ryz[0]; bz = ryz[1];
+    bvx = rv[0]; bvy = rv[1]; bvz = rv[2];
+    gr[k.ball * kRow + 1] = by; gr[k.ball * kRow + 2] = bz;
+    gr[k.ball * kRow + 7] = bvx; gr[k.ball * kRow + 8] = bvy; gr[k.ball * kRow + 9] = bvz;
+    if (k.reset_dof) {
+      float* gd = k.dof + (size_t)env * 2 * D;
+      for (int i = 0; i < 2 * D; ++i) {
+        float v = idof_s[le * L::kSDof + i];
+        dof_s[le * L::kSDof + i] = v;
+        gd[i] = v;
+      }
+    }
+    p_new = 0;
+    k.scratch[0] = 1u;      // some env of the shard reset: the counters get cleared after the step
+  }
+  if (lane_env) {
+    if (phases & (PPK_PHASE_PROGRESS | PPK_PHASE_RESET)) k.progress[env] = p_new;
+    if (phases & PPK_PHASE_REWARD) {
+      k.flags[0][env] = f_pcc; k.flags[1][env] = f_htc; k.flags[2][env] = f_dpc; k.flags[3][env] = f_hdc;
+      k.flags[4][env] = c_closer; k.flags[5][env] = c_hitp; k.flags[6][env] = c_net; k.flags[7][env] = c_table;
+      k.flags[8][env] = c_fall;
+    }
+    if (do_reset) { k.flags[0][env] = 0; k.flags[1][env] = 0; k.flags[2][env] = 0; k.flags[3][env] = 0; }
+  }
+  if (!(phases & PPK_PHASE_OBS)) return;
+
+  // ball in the heading frame (+ y-intersect, ADOF:1833-1839)
+  if (lane < T) {
+    Heading hq; hq.sz = hd[H_SZ]; hq.cw = hd[H_CW];
+    float lp[3], lv[3];
+    rotate_heading(hq, bx - hd[H_RX], by - hd[H_RY], bz - hd[H_RZ], lp[0], lp[1], lp[2]);
+    rotate_heading(hq, bvx, bvy, bvz, lv[0], lv[1], lv[2]);
+    float yi = lp[1] + (lv[1] / (-lv[0] + 1e-6f)) * lp[0];
+    hd[H_BALL0] = lp[0]; hd[H_BALL1] = lp[1]; hd[H_BALL2] = lp[2];
+    hd[H_BALL3] = lv[0]; hd[H_BALL4] = lv[1]; hd[H_BALL5] = lv[2]; hd[H_BALL6] = yi;
+  }
+  __syncwarp();
+
+  // ---- phase P: lane = (env a of the pass, ping-pong body t) ------------------------------------
+  {
+    constexpr int P = 32 / J;
+    const int a = lane / J, t = lane - a * J;
+    const int my_id = k.ids[0][(a < P) ? t : 0];
+#pragma unroll 1
+    for (int pass = 0; pass * P < T; ++pass) {
+      const int e = pass * P + a;
+      const bool ok = (a < P) && (e < nvalid);
+      const int ec = (ok ? e : 0);
+      const float* hh = hdr_s + ec * L::kSHdr;
+      Heading hq; hq.sz = hh[H_SZ]; hq.cw = hh[H_CW];
+      const float* row = rb_s + ec * L::kSRb + my_id * kRow;
+      float lp[3], lv[3];
+      rotate_heading(hq, row[0] - hh[H_RX], row[1] - hh[H_RY], row[2] - hh[H_RZ], lp[0], lp[1], lp[2]);
+      rotate_heading(hq, row[7], row[8], row[9], lv[0], lv[1], lv[2]);
+      float* orow = g_obs + (size_t)e * kAdofObs;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int o = t + i * J;
+        const int src = (a < P ? a * J : 0) + o / 3, comp = o - (o / 3) * 3;
+        float x = __shfl_sync(full, lp[0], src), y = __shfl_sync(full, lp[1], src), z = __shfl_sync(full, lp[2], src);
+        float pv = comp == 0 ? x : (comp == 1 ? y : z);
+        x = __shfl_sync(full, lv[0], src); y = __shfl_sync(full, lv[1], src); z = __shfl_sync(full, lv[2], src);
+        float vv = comp == 0 ? x : (comp == 1 ? y : z);
+        if (ok) { st_stream(orow + o, pv); st_stream(orow + 3 * J + o, vv); }
+      }
+    }
+  }
+  // ---- tail segments, lane = element ------------------------------------------------------------
+  // [60,121): dof_pos, 0.1*dof_vel, ball local pos/vel, y_intersect; [259,313): reference dof pos/vel
+  constexpr int kSegA = 2 * D + 7, kSegB = 2 * D;
+#pragma unroll 1
+  for (int f = lane; f < T * (kSegA + kSegB); f += 32) {
+    int e = f / (kSegA + kSegB), kk = f - e * (kSegA + kSegB);
+    if (e >= nvalid) continue;
+    float v;
+    int o;
+    if (kk < kSegA) {
+      o = 6 * J + kk;
+      if (kk < D) v = dof_s[e * L::kSDof + 2 * kk];
+      else if (kk < 2 * D) v = dof_s[e * L::kSDof + 2 * (kk - D) + 1] * 0.1f;
+      else v = hdr_s[e * L::kSHdr + H_BALL0 + (kk - 2 * D)];
+    } else {
+      int r = kk - kSegA;
+      o = 6 * J + kSegA + 6 * NB + r;
+      v = (r < D) ? idof_s[e * L::kSDof + 2 * r] : idof_s[e * L::kSDof + 2 * (r - D) + 1];
+    }
+    st_stream(g_obs + (size_t)e * kAdofObs + o, v);
+  }
+}
+
+// internal phase bit (host session): the counter clear is issued once per shard, not per chunk
+constexpr uint32_t kPhaseDeferCounterClear = 1u << 8;
+
+inline int launch_adof_clear(unsigned int* scratch, unsigned char* const* flags, long long n, cudaStream_t s) {
+  long long cb = (n / 4 + 255) / 256;
+  if (cb < 1) cb = 1;
+  if (cb > 148 * 8) cb = 148 * 8;
+  adof_clear_counters_kernel<<<(unsigned)cb, 256, 0, s>>>(scratch, flags[4], flags[5], flags[6], flags[7], flags[8], n);
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+
+inline int launch_adof(const KArgs& k, cudaStream_t s) {
+  // staged row windows: live rows 0..39, reference rows 0..27
+  if (k.B < kAdofRbRows) return PPK_ERR_SHAPE;
+  for (int j = 0; j < kAdofJ; ++j)
+    if (k.ids[0][j] >= kAdofRbRows) return PPK_ERR_SHAPE;
+  for (int j = 0; j < kAdofNB; ++j)
+    if (k.bal_ids[j] >= kAdofInitRows) return PPK_ERR_SHAPE;
+  if (k.paddle_body[0] >= kAdofRbRows || k.pelvis_body >= kAdofRbRows) return PPK_ERR_SHAPE;
+  constexpr size_t smem = (size_t)kAdofWarps * AdofLayout::kWarpFloats * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(adof_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return PPK_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  const bool fused_reset = (k.phases & PPK_PHASE_RESET) != 0 && !(k.phases & kPhaseDeferCounterClear);
+  if (fused_reset) {
+    for (int i = 4; i < 9; ++i)
+      if (reinterpret_cast<uintptr_t>(k.flags[i]) & 3u) return PPK_ERR_ALIGN;
+    if (cudaMemsetAsync(k.scratch, 0, sizeof(unsigned int), s) != cudaSuccess) { cudaGetLastError(); return PPK_ERR_LAUNCH; }
+  }
+  const long long tiles = (k.n + kAdofTile - 1) / kAdofTile;
+  const long long blocks = (tiles + kAdofWarps - 1) / kAdofWarps;
+  adof_step_kernel<<<(unsigned)blocks, kAdofWarps * 32, smem, s>>>(k);
+  if (cudaGetLastError() != cudaSuccess) return PPK_ERR_LAUNCH;
+  if (fused_reset) return launch_adof_clear(k.scratch, k.flags, k.n, s);
+  return PPK_OK;
+}
+
+}  // namespace ppk

@@ -1,0 +1,271 @@
+// C ABI (include/ppk.h) over the sm_100a kernels.  No torch types, no allocation, no host sync.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/ppk.h"
+#include "ppk_device.cuh"
+#include "ppk_family.cuh"
+#include "ppk_misc.cuh"
+#include "ppk_adof.cuh"
+
+using namespace ppk;
+
+namespace {
+
+int fill_args(const PpkTask* t, const PpkBuffers* b, uint32_t phases, KArgs* k) {
+  if (t == nullptr || b == nullptr) return PPK_ERR_NULL;
+  if (t->struct_size != sizeof(PpkTask) || b->struct_size != sizeof(PpkBuffers)) return PPK_ERR_ABI;
+  if (t->variant < PPK_BASE || t->variant > PPK_ADOF) return PPK_ERR_VARIANT;
+  if (b->num_envs < 0 || t->num_actors <= 0 || t->num_bodies <= 0 || t->num_dofs <= 0) return PPK_ERR_SHAPE;
+  if (t->num_body_ids < 0 || t->num_body_ids > PPK_MAX_BODY_IDS || t->num_balance_ids < 0 ||
+      t->num_balance_ids > PPK_MAX_BODY_IDS)
+    return PPK_ERR_SHAPE;
+  memset(k, 0, sizeof(*k));
+  k->rb = b->rigid_body_states; k->root = b->root_states; k->dof = b->dof_states; k->force = b->dof_forces;
+  k->pre = b->pre_ball_states; k->init_root = b->initial_root_states; k->init_dof = b->initial_dof_states;
+  k->init_rb = b->initial_body_states; k->reset_vel = b->reset_ball_vel; k->reset_yz = b->reset_ball_pos_yz;
+  k->obs = b->obs_buf; k->rew = b->rew_buf;
+  k->reset = reinterpret_cast<long long*>(b->reset_buf);
+  k->progress = reinterpret_cast<long long*>(b->progress_buf);
+  for (int i = 0; i < PPK_MAX_FLAGS; ++i) k->flags[i] = b->flags[i];
+  k->stats = b->stats; k->scratch = b->scratch;
+  k->n = b->num_envs; k->max_len = t->max_episode_length;
+  k->pre_stride = b->pre_ball_stride; k->pre_vx = b->pre_vx_offset; k->pre_vz = b->pre_vz_offset;
+  k->A = t->num_actors; k->B = t->num_bodies; k->D = t->num_dofs;
+  for (int h = 0; h < 2; ++h) {
+    k->hum[h] = t->humanoid_actor[h];
+    k->paddle_body[h] = t->paddle_body[h];
+    k->paddle_j[h] = -1;
+    for (int j = 0; j < t->num_body_ids; ++j) {
+      int id = t->body_ids[h][j];
+      if (h == 0 || t->variant == PPK_A4) {
+        if (id < 0 || id >= t->num_bodies) return PPK_ERR_SHAPE;
+      }
+      k->ids[h][j] = id;
+      if (id == t->paddle_body[h]) k->paddle_j[h] = j;
+    }
+    if (t->paddle_body[h] < 0 || t->paddle_body[h] >= t->num_bodies) return PPK_ERR_SHAPE;
+    if (t->humanoid_actor[h] < 0 || t->humanoid_actor[h] >= t->num_actors) return PPK_ERR_SHAPE;
+  }
+  for (int j = 0; j < t->num_balance_ids; ++j) {
+    if (t->balance_ids[j] < 0 || t->balance_ids[j] >= t->num_bodies) return PPK_ERR_SHAPE;
+    k->bal_ids[j] = t->balance_ids[j];
+  }
+  k->ball = t->ball_actor; k->pelvis_body = t->pelvis_body;
+  if (t->ball_actor < 0 || t->ball_actor >= t->num_actors) return PPK_ERR_SHAPE;
+  if (t->pelvis_body < 0 || t->pelvis_body >= t->num_bodies) return PPK_ERR_SHAPE;
+  k->alpha = t->alpha; k->power_coef = t->power_coefficient; k->penalty = t->penalty;
+  k->hit_table = t->hit_table_reward; k->not_hit = t->not_hit_table_penalty; k->cross_net = t->cross_net_reward;
+  k->die_penalty = t->die_penalty; k->hit_paddle = t->hit_paddle_reward; k->miss_coef = t->miss_paddle_penalty_coefficient;
+  k->term_dist = t->is_train ? 0.32f : 1e6f;           // ADOF:1404-1410, is_g1 branch
+  k->phases = (int)phases; k->write_flags = t->write_flags; k->reset_dof = t->reset_dof;
+  return PPK_OK;
+}
+
+inline bool misaligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
+
+int num_flags_of(int variant) {
+  switch (variant) {
+    case PPK_TILT: return 3;
+    case PPK_A4: return 6;
+    case PPK_NES: return 2;
+    case PPK_ALIGN: return 1;
+    case PPK_ADOF: return 9;
+    default: return 0;
+  }
+}
+
+// Pointers a given phase set dereferences; NULL or misaligned ones are rejected before the launch.
+int check_step_pointers(const PpkTask* t, const PpkBuffers* b, uint32_t phases) {
+  const int v = t->variant;
+  const bool rew = phases & PPK_PHASE_REWARD, rst = phases & PPK_PHASE_RESET, obs = phases & PPK_PHASE_OBS;
+  if (!b->rigid_body_states || !b->root_states || !b->dof_states || !b->progress_buf || !b->reset_buf) return PPK_ERR_NULL;
+  if (v != PPK_BASE && !b->dof_forces) return PPK_ERR_NULL;
+  if (rew && !b->rew_buf) return PPK_ERR_NULL;
+  if (rew && v != PPK_BASE && !b->pre_ball_states) return PPK_ERR_NULL;
+  if (obs && !b->obs_buf) return PPK_ERR_NULL;
+  if (rst && (!b->initial_root_states || !b->reset_ball_vel)) return PPK_ERR_NULL;
+  if (rst && t->reset_dof && !b->initial_dof_states) return PPK_ERR_NULL;
+  if (v == PPK_ADOF) {
+    if (!b->initial_body_states || !b->initial_dof_states) return PPK_ERR_NULL;
+    if (rst && (!b->reset_ball_pos_yz || !b->scratch)) return PPK_ERR_NULL;
+  }
+  if ((phases & PPK_PHASE_STATS) && !b->stats) return PPK_ERR_NULL;
+  if (rew || rst)
+    for (int i = 0; i < num_flags_of(v); ++i)
+      if (!b->flags[i]) return PPK_ERR_NULL;
+  const void* f32[] = {b->rigid_body_states, b->root_states, b->dof_states, b->dof_forces, b->pre_ball_states,
+                       b->initial_root_states, b->initial_dof_states, b->initial_body_states, b->reset_ball_vel,
+                       b->reset_ball_pos_yz, b->obs_buf, b->rew_buf};
+  for (const void* p : f32)
+    if (p && misaligned(p, 4)) return PPK_ERR_ALIGN;
+  if (misaligned(b->progress_buf, 8) || misaligned(b->reset_buf, 8)) return PPK_ERR_ALIGN;
+  if (b->stats && misaligned(b->stats, 8)) return PPK_ERR_ALIGN;
+  if (rew && v != PPK_BASE && (b->pre_ball_stride <= 0 || b->pre_vx_offset < 0 || b->pre_vx_offset >= b->pre_ball_stride))
+    return PPK_ERR_SHAPE;
+  if (rew && v == PPK_ALIGN && (b->pre_vz_offset < 0 || b->pre_vz_offset >= b->pre_ball_stride)) return PPK_ERR_SHAPE;
+  return PPK_OK;
+}
+
+template <int V, int H, int J, int D, int A, int TILE>
+int launch_family(const KArgs& k, cudaStream_t s) {
+  using L = FamilyLayout<H, J, D, A, TILE>;
+  auto kern = family_step_kernel<V, H, J, D, A, TILE>;
+  constexpr size_t smem = (size_t)kFamilyWarps * L::kWarpFloats * sizeof(float);
+  static bool configured = false;        // idempotent attribute; a benign race sets it twice
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return PPK_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  const long long tiles = (k.n + TILE - 1) / TILE;
+  const long long blocks = (tiles + kFamilyWarps - 1) / kFamilyWarps;
+  kern<<<(unsigned)blocks, kFamilyWarps * 32, smem, s>>>(k);
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ppk_abi_version(void) { return PPK_ABI_VERSION; }
+
+const char* ppk_strerror(int code) {
+  switch (code) {
+    case PPK_OK: return "ok";
+    case PPK_ERR_NULL: return "a required device pointer is NULL";
+    case PPK_ERR_SHAPE: return "sizes are inconsistent with the task variant";
+    case PPK_ERR_ALIGN: return "a pointer is not aligned to its element type";
+    case PPK_ERR_VARIANT: return "unknown task variant or unsupported phase";
+    case PPK_ERR_LAUNCH: return "CUDA kernel launch failed";
+    case PPK_ERR_ABI: return "struct_size mismatch: header and library disagree";
+    case PPK_ERR_CUDA: return "a CUDA runtime call failed";
+    default: return "unknown ppk error";
+  }
+}
+
+int ppk_post_physics_step(const PpkTask* t, const PpkBuffers* b, uint32_t phases, void* stream) {
+  KArgs k;
+  int rc = fill_args(t, b, phases, &k);
+  if (rc != PPK_OK) return rc;
+  if ((phases & ~((uint32_t)PPK_PHASE_ALL | kPhaseDeferCounterClear)) != 0 || (phases & PPK_PHASE_ALL) == 0)
+    return PPK_ERR_VARIANT;
+  rc = check_step_pointers(t, b, phases);
+  if (rc != PPK_OK) return rc;
+  if (b->num_envs == 0) return PPK_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (t->variant) {
+    case PPK_BASE: {
+      if (t->num_actors < 5 || t->ball_actor + 1 >= t->num_actors) return PPK_ERR_SHAPE;
+      const long long blocks = ((b->num_envs + 31) / 32 + kBaseWarps - 1) / kBaseWarps;
+      base_step_kernel<<<(unsigned)blocks, kBaseWarps * 32, 0, s>>>(k);
+      return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+    }
+    case PPK_A3:
+    case PPK_TILT:
+    case PPK_NES:
+    case PPK_ALIGN:
+      if (t->num_actors != 3 || t->num_dofs != 7 || t->num_body_ids != 10) return PPK_ERR_SHAPE;
+      if (t->variant == PPK_A3) return launch_family<PPK_A3, 1, 10, 7, 3, 32>(k, s);
+      if (t->variant == PPK_TILT) return launch_family<PPK_TILT, 1, 10, 7, 3, 32>(k, s);
+      if (t->variant == PPK_NES) return launch_family<PPK_NES, 1, 10, 7, 3, 32>(k, s);
+      return launch_family<PPK_ALIGN, 1, 10, 7, 3, 32>(k, s);
+    case PPK_A4:
+      if (t->num_actors != 4 || t->num_dofs != 14 || t->num_body_ids != 10) return PPK_ERR_SHAPE;
+      return launch_family<PPK_A4, 2, 10, 14, 4, 16>(k, s);
+    case PPK_ADOF:
+      if (t->num_actors != 3 || t->num_dofs != 27 || t->num_body_ids != 10 || t->num_balance_ids != 23) return PPK_ERR_SHAPE;
+      return launch_adof(k, s);
+    default:
+      return PPK_ERR_VARIANT;
+  }
+}
+
+int ppk_compute_reward(const PpkTask* t, const PpkBuffers* b, void* stream) {
+  return ppk_post_physics_step(t, b, PPK_PHASE_REWARD, stream);
+}
+
+int ppk_compute_observations(const PpkTask* t, const PpkBuffers* b, void* stream) {
+  return ppk_post_physics_step(t, b, PPK_PHASE_OBS, stream);
+}
+
+int ppk_reset_idx(const PpkTask* t, const PpkBuffers* b, const int64_t* env_ids, int64_t num_ids, const float* ball_vel,
+                  const float* ball_pos_yz, const int64_t* actor_indices, const int64_t* dof_indices,
+                  int32_t dof_indices_per_env, int32_t* actor_indices_out, int32_t* dof_indices_out, void* stream) {
+  KArgs k;
+  int rc = fill_args(t, b, PPK_PHASE_RESET, &k);
+  if (rc != PPK_OK) return rc;
+  if (num_ids < 0) return PPK_ERR_SHAPE;
+  if (num_ids == 0) return PPK_OK;
+  if (!env_ids || !b->root_states || !b->initial_root_states || !b->progress_buf) return PPK_ERR_NULL;
+  if (t->reset_dof && (!b->dof_states || !b->initial_dof_states)) return PPK_ERR_NULL;
+  if (!ball_vel && !b->reset_ball_vel) return PPK_ERR_NULL;
+  if (t->variant == PPK_ADOF && !ball_pos_yz && !b->reset_ball_pos_yz) return PPK_ERR_NULL;
+  if (t->variant == PPK_BASE && (!ball_vel || !b->reset_buf)) return PPK_ERR_NULL;
+  if (actor_indices_out && !actor_indices) return PPK_ERR_NULL;
+  if (dof_indices_out && (!dof_indices || dof_indices_per_env <= 0 || dof_indices_per_env > 32)) return PPK_ERR_SHAPE;
+  if (t->num_actors > 32) return PPK_ERR_SHAPE;
+  if (misaligned(env_ids, 8)) return PPK_ERR_ALIGN;
+  ResetArgs r;
+  memset(&r, 0, sizeof(r));
+  r.env_ids = reinterpret_cast<const long long*>(env_ids); r.num_ids = num_ids;
+  r.ball_vel = ball_vel; r.ball_yz = ball_pos_yz;
+  r.actor_indices = reinterpret_cast<const long long*>(actor_indices);
+  r.dof_indices = reinterpret_cast<const long long*>(dof_indices);
+  r.dof_per_env = dof_indices_out ? dof_indices_per_env : 0;
+  r.actor_out = actor_indices_out; r.dof_out = dof_indices_out;
+  r.variant = t->variant;
+  // flags written by _reset_idx: TILT:902-905, NES:913-917, ALIGN:897, A4:908-911, ADOF:1023-1026
+  // (ADOF resets only its four *_calculated flags; the five counters are cleared elsewhere)
+  int nf = num_flags_of(t->variant);
+  if (t->variant == PPK_ADOF) nf = 4;
+  r.num_flags = nf;
+  for (int i = 0; i < nf; ++i) {
+    if (!b->flags[i]) return PPK_ERR_NULL;
+    r.flag_reset_value[i] = ((t->variant == PPK_TILT || t->variant == PPK_A4) && (i % 3) == 2) ? 1 : 0;
+  }
+  const int warps = 4;
+  const long long blocks = (num_ids + warps - 1) / warps;
+  reset_idx_kernel<<<(unsigned)blocks, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(k, r);
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+
+int ppk_pre_physics_step(const PpkTask* t, const PpkBuffers* b, void* stream) {
+  if (t == nullptr || b == nullptr) return PPK_ERR_NULL;
+  if (t->struct_size != sizeof(PpkTask) || b->struct_size != sizeof(PpkBuffers)) return PPK_ERR_ABI;
+  if (!b->actions || !b->pd_action_offset || !b->pd_action_scale || !b->pd_targets) return PPK_ERR_NULL;
+  const bool save_ball = t->variant != PPK_BASE;          // BASE:581-585 has no ball clone
+  if (save_ball && (!b->pre_ball_states || !b->root_states)) return PPK_ERR_NULL;
+  if (save_ball && (b->pre_ball_stride <= 0 || b->pre_vx_offset < 0 || b->pre_vx_offset >= b->pre_ball_stride ||
+                    b->pre_vz_offset >= b->pre_ball_stride))
+    return PPK_ERR_SHAPE;
+  if (b->num_envs < 0 || t->num_dofs <= 0) return PPK_ERR_SHAPE;
+  if (b->num_envs == 0) return PPK_OK;
+  const long long total = b->num_envs * t->num_dofs;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pre_step_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      b->actions, b->pd_action_offset, b->pd_action_scale, b->pd_targets, b->num_envs, t->num_dofs, b->root_states,
+      t->num_actors * kRow, t->ball_actor, save_ball ? b->pre_ball_states : nullptr, b->pre_ball_stride,
+      b->pre_vx_offset, b->pre_vz_offset);
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+
+// Used by the host session: the shard-wide ADOF counter clear after all chunks ran (ADOF:1162-1175).
+int ppk_internal_adof_clear(const PpkBuffers* b, void* stream) {
+  if (!b || !b->scratch) return PPK_ERR_NULL;
+  for (int i = 4; i < 9; ++i)
+    if (!b->flags[i] || misaligned(b->flags[i], 4)) return PPK_ERR_ALIGN;
+  return launch_adof_clear(b->scratch, b->flags, b->num_envs, static_cast<cudaStream_t>(stream));
+}
+
+int ppk_stats_reduce(double* stats, double* out, void* stream) {
+  if (!stats || !out) return PPK_ERR_NULL;
+  stats_reduce_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(stats, out);
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// Device-side building blocks of the ping-pong task step (sm_100a).
+//
+// Compiled with -fmad=false: every flag of the reference is a comparison of fp32
+// values produced by single correctly-rounded ATen ops, so contraction into FMA
+// would change which side of a threshold a value lands on.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ppk.h"
+
+namespace ppk {
+
+constexpr int kRow = 13;  // floats per rigid-body / root-state row: pos3 quat4 linvel3 angvel3
+
+// Kernel arguments: the two C structs flattened, by value in param space.
+struct KArgs {
+  const float* rb;
+  float* root;
+  float* dof;
+  const float* force;
+  const float* pre;
+  const float* init_root;
+  const float* init_dof;
+  const float* init_rb;
+  const float* reset_vel;
+  const float* reset_yz;
+  float* obs;
+  float* rew;
+  long long* reset;
+  long long* progress;
+  unsigned char* flags[PPK_MAX_FLAGS];
+  double* stats;
+  unsigned int* scratch;
+  long long n;
+  long long max_len;
+  int pre_stride, pre_vx, pre_vz;
+  int A, B, D;
+  int hum[2];
+  int ball;
+  int paddle_body[2];
+  int paddle_j[2];   // index of the paddle row inside ids (or -1: load it from global)
+  int pelvis_body;
+  int ids[2][PPK_MAX_BODY_IDS];
+  int bal_ids[PPK_MAX_BODY_IDS];
+  float alpha, power_coef, penalty, hit_table, not_hit, cross_net, die_penalty, hit_paddle, miss_coef;
+  float term_dist;
+  int phases;
+  int write_flags;
+  int reset_dof;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming loads/stores: every byte of state is touched once per step
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+
+// ---- heading frame -------------------------------------------------------------------------
+// calc_heading_quat_inv(q) of torch_jit_utils, restated op by op (oracle/jit_utils_restated.py):
+//   rot = my_quat_rotate(q, (1,0,0)); heading = atan2(rot.y, rot.x);
+//   hq  = quat_unit([0, 0, sin(-heading/2), cos(-heading/2)])
+// The heading quaternion only has z and w components (x, y are exact zeros).
+struct Heading {
+  float sz, cw;
+};
+
+__device__ __forceinline__ Heading heading_quat_inv(float qx, float qy, float qz, float qw) {
+  // a = v*(2 w^2 - 1) with v = (1,0,0);  b = cross(q_vec, v)*w*2 = (0, qz*w*2, -qy*w*2);
+  // c = q_vec*(q_vec . v)*2 = (qx*qx*2, qy*qx*2, qz*qx*2);  rot = (a + b) + c
+  float a0 = 2.0f * (qw * qw) - 1.0f;
+  float rx = (a0 + 0.0f) + (qx * qx) * 2.0f;
+  float ry = (0.0f + (qz * qw) * 2.0f) + (qy * qx) * 2.0f;
+  float heading = atan2f(ry, rx);
+  float half = (-heading) / 2.0f;
+  float s = sinf(half);
+  float c = cosf(half);
+  float nrm = sqrtf(s * s + c * c);
+  nrm = fmaxf(nrm, 1e-9f);
+  Heading h;
+  h.sz = s / nrm;
+  h.cw = c / nrm;
+  return h;
+}
+
+// my_quat_rotate((0,0,sz,cw), v):  a + b + c with the zero components dropped
+__device__ __forceinline__ void rotate_heading(const Heading& h, float vx, float vy, float vz, float& ox, float& oy,
+                                               float& oz) {
+  float a0 = 2.0f * (h.cw * h.cw) - 1.0f;
+  float bx = ((-(h.sz * vy)) * h.cw) * 2.0f;
+  float by = ((h.sz * vx) * h.cw) * 2.0f;
+  float cz = (h.sz * (h.sz * vz)) * 2.0f;
+  ox = vx * a0 + bx;
+  oy = vy * a0 + by;
+  oz = vz * a0 + cz;
+}
+
+// ---- rewards --------------------------------------------------------------------------------
+struct Scene {  // what the reward functions read, one env
+  float bx, by, bz, vx, vz;   // ball position / velocity (root row)
+  float pre_vx, pre_vz;       // ball velocity saved by pre_physics_step
+  float px, py, pz;           // paddle position (rigid-body row)
+  float hx;                   // humanoid root x
+  float power_reward;         // -power_coefficient * sum|force*dof_vel|
+  long long progress;         // after the +1
+};
+
+__device__ __forceinline__ float dist3(const Scene& s) {
+  float dx = s.px - s.bx, dy = s.py - s.by, dz = s.pz - s.bz;
+  return sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+// A3:1080-1173
+__device__ __forceinline__ float reward_a3(const Scene& s, const KArgs& k, bool& die) {
+  float d = dist3(s);
+  float pos = 1.0f / (1.0f + 1.5f * d * d);
+  bool hit = (s.pre_vx < 0.0f) && (s.vx > 0.0f);
+  float vel = hit ? k.alpha * fabsf(s.vx) : 0.0f;
+  float r = (pos + s.power_reward) + vel;
+  bool missed = s.bx < s.px - 1e-3f;
+  if (missed) r = r + k.penalty;
+  die = missed || (s.bz < 0.1f);
+  return r;
+}
+
+// TILT:1105-1270 / A4:1113-1278 (MIRROR=false), A4:1280-1439 (MIRROR=true)
+template <bool MIRROR>
+__device__ __forceinline__ float reward_tilt(const Scene& s, const KArgs& k, bool& cc, bool& rc, bool& nbbh, bool& die) {
+  float d = dist3(s);
+  float pos = 1.0f / (1.0f + 1.5f * d * d);
+  bool outgoing = MIRROR ? (s.vx < 0.0f) : (s.vx > 0.0f);
+  bool cond = (MIRROR ? (s.pre_vx > 0.0f) : (s.pre_vx < 0.0f)) && outgoing;
+  float vel = (cond && !cc) ? k.alpha * fabsf(s.vx) : 0.0f;
+  cc = cc || cond;
+  bool missed = MIRROR ? (s.bx > s.hx + 0.05f) : (s.bx < s.hx - 0.05f);
+  float r = missed ? (0.0f + k.penalty) : 0.0f;
+  bool bounce_up = (s.bz < 0.83f) && outgoing && (s.by < 0.6f) && (s.by > -0.6f);
+  bool near_half = MIRROR ? (s.bx > 1.06f) : (s.bx < 2.44f);
+  bool far_table = MIRROR ? ((s.bx < 1.06f) && (s.bx > 0.4f)) : ((s.bx > 2.44f) && (s.bx < 3.1f));
+  bool beyond = MIRROR ? (s.bx <= 0.4f) : (s.bx >= 3.1f);
+  bool stage_a = near_half && bounce_up;
+  float hit = (stage_a && !rc) ? k.not_hit : 0.0f;
+  rc = rc || stage_a;
+  nbbh = nbbh && !stage_a;
+  bool stage_b = far_table && bounce_up && nbbh;
+  if (stage_b && !rc) hit = k.hit_table;
+  rc = rc || stage_b;
+  if (beyond && outgoing && !rc) hit = k.not_hit;
+  rc = rc || beyond;
+  bool over_net = (s.bx > 1.7f) && (s.bx < 1.8f) && outgoing && (s.by < 0.4f) && (s.by > -0.4f) && (s.bz > 0.98f) &&
+                  (s.bz < 1.14f);
+  float net = over_net ? 400.0f : 0.0f;
+  r = r + ((((pos + s.power_reward) + vel) + hit) + net);
+  die = s.bz < 0.1f;
+  return r;
+}
+
+// NES:1115-1322
+__device__ __forceinline__ float reward_nes(const Scene& s, const KArgs& k, bool& pcc, bool& mbc, bool& die) {
+  bool hit = (s.pre_vx < 0.0f) && (s.vx > 1.0f);
+  bool behind = s.bx < s.hx - 0.05f;
+  bool missed = behind || (s.bx < s.px - 0.1f);
+  float r = (!mbc && missed) ? (0.0f + k.penalty) : 0.0f;
+  mbc = mbc || missed;
+  float dy = s.py - s.by, dz = s.pz - s.bz;
+  float d = sqrtf(dy * dy + dz * dz);
+  float pos = (!pcc || behind) ? 1.0f * expf((-20.0f * d) * d) : 0.0f;
+  float vel = (hit && !pcc) ? k.alpha * fabsf(s.vx) : 0.0f;
+  pcc = pcc || hit;
+  r = r + ((pos + s.power_reward) + vel);
+  if (s.bz < 0.1f) r = -800.0f + r;
+  die = false;
+  return r;
+}
+
+// ALIGN:1097-1230
+__device__ __forceinline__ float reward_align(const Scene& s, const KArgs& k, bool& rc, bool& die) {
+  float d = dist3(s);
+  float pos = 1.0f / (1.0f + 1.5f * d * d);
+  bool cond = (s.pre_vx < 0.0f) && (s.vx > 0.0f);
+  float vel = cond ? k.alpha * fabsf(s.vx) : 0.0f;
+  bool in_table = (s.bx > 2.2f) && (s.bx < 3.1f);
+  bool bounce_up = (s.pre_vz < 0.0f) && (s.vz > 0.0f);
+  bool no_bounce_before_half = (s.bx < 2.2f) && !bounce_up;
+  bool award = in_table && bounce_up && no_bounce_before_half;
+  float hit = (award && !rc) ? k.hit_table : 0.0f;
+  rc = rc || award;
+  if ((s.bx >= 3.1f) && (s.vx > 0.0f) && !rc) hit = k.not_hit;
+  rc = rc || (s.bx >= 3.1f);
+  float r = ((pos + s.power_reward) + vel) + hit;
+  if (s.bx < s.hx - 0.05f) r = r + k.penalty;
+  die = s.bz < 0.1f;
+  return r;
+}
+
+}  // namespace ppk

@@ -1,0 +1,206 @@
+// Small kernels around the fused step: BASE variant, pre_physics_step, reset_idx, statistics.
+#pragma once
+#include "ppk_device.cuh"
+
+namespace ppk {
+
+// ---- BASE (humanoid_pingpong.py) -----------------------------------------------------------------
+// post_physics_step order BASE:587-596: progress += 1 -> reset_idx(envs whose reset_buf is set)
+// -> compute_observations -> compute_reward.  No rotation: the obs row is a gather of pos/vel of
+// paddle1, paddle2, ball1, ball2 (BASE:776-813).
+constexpr int kBaseWarps = 4;
+constexpr int kBaseObs = 24;
+
+__global__ void __launch_bounds__(kBaseWarps * 32)
+base_step_kernel(const __grid_constant__ KArgs k) {
+  __shared__ float obs_s[kBaseWarps][32 * (kBaseObs + 1)];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long env0 = ((long long)blockIdx.x * kBaseWarps + warp) * 32;
+  if (env0 >= k.n) return;
+  const int nvalid = (int)min(32LL, k.n - env0);
+  const bool on = lane < nvalid;
+  const long long env = env0 + (on ? lane : 0);
+  const int phases = k.phases;
+  const int rootN = k.A * kRow;
+
+  long long prog = k.progress[env] + ((phases & PPK_PHASE_PROGRESS) ? 1 : 0);
+  float* gr = k.root + (size_t)env * rootN;
+  // reset_idx of the envs flagged by the PREVIOUS step's reward (BASE:589-591)
+  if ((phases & PPK_PHASE_RESET) && on && k.reset[env] != 0) {
+    const float* ir = k.init_root + (size_t)env * rootN;
+    for (int a = 0; a < k.A; ++a)
+      for (int c = 0; c < 7; ++c) gr[a * kRow + c] = ir[a * kRow + c];     // velocities are NOT zeroed (BASE:533-534)
+    for (int c = 0; c < 3; ++c) {
+      gr[k.ball * kRow + 7 + c] = k.reset_vel[c];              // ball1 <- velocity_1 (BASE:549)
+      gr[(k.ball + 1) * kRow + 7 + c] = k.reset_vel[3 + c];    // ball2 <- velocity_2 (BASE:550)
+    }
+    const float* id = k.init_dof + (size_t)env * 2 * k.D;
+    float* gd = k.dof + (size_t)env * 2 * k.D;
+    for (int i = 0; i < 2 * k.D; ++i) gd[i] = id[i];
+    prog = 0;
+  }
+  if (on && (phases & (PPK_PHASE_PROGRESS | PPK_PHASE_RESET))) k.progress[env] = prog;
+
+  const float* p1 = k.rb + ((size_t)env * k.B + k.paddle_body[0]) * kRow;
+  const float* p2 = k.rb + ((size_t)env * k.B + k.paddle_body[1]) * kRow;
+  const float* b1 = gr + k.ball * kRow;
+  const float* b2 = gr + (k.ball + 1) * kRow;
+  float o[kBaseObs];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    o[c] = p1[c]; o[3 + c] = p1[7 + c];
+    o[6 + c] = p2[c]; o[9 + c] = p2[7 + c];
+    o[12 + c] = b1[c]; o[15 + c] = b1[7 + c];
+    o[18 + c] = b2[c]; o[21 + c] = b2[7 + c];
+  }
+  if (phases & PPK_PHASE_OBS) {
+#pragma unroll
+    for (int c = 0; c < kBaseObs; ++c) obs_s[warp][lane * (kBaseObs + 1) + c] = o[c];
+    __syncwarp();
+    float* g = k.obs + (size_t)env0 * kBaseObs;
+#pragma unroll
+    for (int i = 0; i < kBaseObs; ++i) {
+      int f = i * 32 + lane, e = f / kBaseObs, c = f - e * kBaseObs;
+      if (e < nvalid) st_stream(g + f, obs_s[warp][e * (kBaseObs + 1) + c]);
+    }
+  }
+  if (phases & PPK_PHASE_REWARD) {
+    // BASE:622-667: d1 = paddle1 <-> ball2, d2 = paddle2 <-> ball1
+    float dx = o[0] - o[18], dy = o[1] - o[19], dz = o[2] - o[20];
+    float d1 = sqrtf(dx * dx + dy * dy + dz * dz);
+    dx = o[6] - o[12]; dy = o[7] - o[13]; dz = o[8] - o[14];
+    float d2 = sqrtf(dx * dx + dy * dy + dz * dz);
+    float r = 1.0f / (1.0f + d1 * d1) + 1.0f / (1.0f + d2 * d2);
+    bool die = (o[14] < 0.1f) && (o[14] < 0.1f);          // ball1 tested twice (BASE:662)
+    bool rst = (prog >= k.max_len - 1) || die;
+    if (on) { k.rew[env] = r; k.reset[env] = rst ? 1 : 0; }
+    if (phases & PPK_PHASE_STATS) {
+      double s0 = warp_sum(on ? (double)r : 0.0), s1 = warp_sum(on ? (double)prog : 0.0), s2 = warp_sum((on && rst) ? 1.0 : 0.0);
+      if (lane == 0) {
+        double* slot = k.stats + (size_t)((env0 / 32) % PPK_STATS_SLOTS) * PPK_NUM_STATS;
+        atomicAdd(slot + PPK_STAT_REWARD, s0); atomicAdd(slot + PPK_STAT_PROGRESS, s1); atomicAdd(slot + PPK_STAT_RESETS, s2);
+      }
+    }
+  }
+}
+
+// ---- pre_physics_step (TILT:1002-1020) ---------------------------------------------------------------
+// pd_tar[n,d] = offset[d] + scale[d]*actions[n,d]; save the ball's vx (and vz) for the next reward.
+__global__ void __launch_bounds__(256)
+pre_step_kernel(const float* __restrict__ actions, const float* __restrict__ offset, const float* __restrict__ scale,
+                float* __restrict__ pd, long long n, int D, const float* __restrict__ root, int rootN, int ball,
+                float* __restrict__ pre, int pre_stride, int pre_vx, int pre_vz) {
+  const long long total = n * D;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int d = (int)(i % D);
+    st_stream(pd + i, offset[d] + scale[d] * ld_stream(actions + i));
+  }
+  if (pre != nullptr) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+      const float* b = root + (size_t)e * rootN + ball * kRow;
+      if (pre_stride == kRow) {          // the reference's full-row clone (TILT:1020)
+        for (int c = 0; c < kRow; ++c) pre[(size_t)e * kRow + c] = b[c];
+      } else {
+        pre[(size_t)e * pre_stride + pre_vx] = b[7];
+        if (pre_vz >= 0 && pre_vz != pre_vx) pre[(size_t)e * pre_stride + pre_vz] = b[9];
+      }
+    }
+  }
+}
+
+// ---- reset_idx(env_ids) (TILT:847-906 and variants) ------------------------------------------------
+// One warp per listed env: rewrite its root rows / DOF rows from the initial tensors, launch the
+// ball, clear progress and flags, and gather the int32 actor / dof indices for the gym setters.
+struct ResetArgs {
+  const long long* env_ids;
+  long long num_ids;
+  const float* ball_vel;       // [k,3] (BASE [2,3]) or nullptr -> rows env_id of reset_vel
+  const float* ball_yz;        // [k,2] ADOF or nullptr -> rows env_id of reset_yz
+  const long long* actor_indices;
+  const long long* dof_indices;
+  int dof_per_env;
+  int* actor_out;
+  int* dof_out;
+  int num_flags;               // flags written at reset
+  int flag_reset_value[PPK_MAX_FLAGS];
+  int variant;
+};
+
+__global__ void __launch_bounds__(128)
+reset_idx_kernel(const __grid_constant__ KArgs k, const __grid_constant__ ResetArgs r) {
+  const int lane = threadIdx.x & 31;
+  const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= r.num_ids) return;
+  const long long env = r.env_ids[i];
+  if (env < 0 || env >= k.n) return;
+  const int rootN = k.A * kRow;
+  const bool base = r.variant == PPK_BASE;
+  const float* ir = k.init_root + (size_t)env * rootN;
+  float* gr = k.root + (size_t)env * rootN;
+  for (int f = lane; f < rootN; f += 32) {
+    int c = f % kRow;
+    if (c < 7) gr[f] = ir[f];
+    else if (!base) gr[f] = 0.0f;
+  }
+  __syncwarp();
+  if (lane < 3) {
+    if (base) {
+      gr[k.ball * kRow + 7 + lane] = r.ball_vel[lane];
+      gr[(k.ball + 1) * kRow + 7 + lane] = r.ball_vel[3 + lane];
+    } else {
+      const float* bv = r.ball_vel ? r.ball_vel + (size_t)i * 3 : k.reset_vel + (size_t)env * 3;
+      gr[k.ball * kRow + 7 + lane] = bv[lane];
+    }
+  }
+  if (r.variant == PPK_ADOF && lane < 2) {
+    const float* yz = r.ball_yz ? r.ball_yz + (size_t)i * 2 : k.reset_yz + (size_t)env * 2;
+    gr[k.ball * kRow + 1 + lane] = yz[lane];
+  }
+  if (k.reset_dof) {
+    const float* id = k.init_dof + (size_t)env * 2 * k.D;
+    float* gd = k.dof + (size_t)env * 2 * k.D;
+    for (int f = lane; f < 2 * k.D; f += 32) gd[f] = id[f];
+  }
+  if (lane == 0) {
+    k.progress[env] = 0;
+    if (base) k.reset[env] = 0;                      // BASE:579
+  }
+  if (lane < r.num_flags) k.flags[lane][env] = (unsigned char)r.flag_reset_value[lane];
+  if (r.actor_out != nullptr && lane < k.A) r.actor_out[i * k.A + lane] = (int)r.actor_indices[env * k.A + lane];
+  if (r.dof_out != nullptr && lane < r.dof_per_env)
+    r.dof_out[i * r.dof_per_env + lane] = (int)r.dof_indices[env * r.dof_per_env + lane];
+}
+
+// ---- statistics ----------------------------------------------------------------------------------
+__global__ void stats_reduce_kernel(double* stats, double* out) {
+  const int s = threadIdx.x;
+  if (s >= PPK_NUM_STATS) return;
+  double acc = 0.0;
+  for (int slot = 0; slot < PPK_STATS_SLOTS; ++slot) {
+    acc += stats[slot * PPK_NUM_STATS + s];
+    stats[slot * PPK_NUM_STATS + s] = 0.0;
+  }
+  out[s] = acc;
+}
+
+// ADOF:1162-1175: when any env of the shard reset this step, all five counters are cleared.
+__global__ void __launch_bounds__(256)
+adof_clear_counters_kernel(const unsigned int* any_reset, unsigned char* c0, unsigned char* c1, unsigned char* c2,
+                           unsigned char* c3, unsigned char* c4, long long n) {
+  if (*any_reset == 0u) return;
+  const long long words = (n + 3) / 4;    // tensors are at least 4-byte aligned allocations; tail handled bytewise
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) {
+    long long b = i * 4;
+    if (b + 4 <= n) {
+      *reinterpret_cast<unsigned int*>(c0 + b) = 0u; *reinterpret_cast<unsigned int*>(c1 + b) = 0u;
+      *reinterpret_cast<unsigned int*>(c2 + b) = 0u; *reinterpret_cast<unsigned int*>(c3 + b) = 0u;
+      *reinterpret_cast<unsigned int*>(c4 + b) = 0u;
+    } else {
+      for (long long j = b; j < n; ++j) { c0[j] = 0; c1[j] = 0; c2[j] = 0; c3[j] = 0; c4[j] = 0; }
+    }
+  }
+}
+
+}  // namespace ppk

@@ -1,0 +1,212 @@
+"""Host-side mirror of the reference's task classes (tasks/humanoid_pingpong*.py) over libppk.so.
+
+Same method names, argument meaning and call order as the reference:
+    pre_physics_step(actions)   TILT:1002-1020
+    post_physics_step()         TILT:1022-1052   (one fused kernel here)
+    compute_reward(actions)     TILT:739-768
+    compute_observations()      TILT:770-799
+    reset_idx(env_ids)          TILT:809/847-906
+and the same attribute names for the buffers and flag tensors (`obs_buf`, `rew_buf`, `reset_buf`,
+`progress_buf`, `condition_calculated`, ...).  PhysX is replaced by a dict of synthetic state
+tensors (`synth.make_state`); everything numerical happens in the CUDA library -- there is no
+torch or CPU fallback, a missing library raises.
+"""
+from typing import Dict, Optional
+
+import torch
+
+from . import _native as N
+from .config import CONFIGS, TaskConfig
+from .stats import EpisodeStats
+from .vec_task import VecTask
+
+_STATE_KEYS = ("rigid_body_states", "root_states", "dof_states", "dof_forces", "initial_root_states",
+               "initial_dof_states", "initial_body_states", "reset_ball_vel", "reset_ball_pos_yz",
+               "pd_action_offset", "pd_action_scale", "actor_indices", "dof_indices")
+
+
+class PingpongTask(VecTask):
+    """Generic task over one variant; the named subclasses below only pick the variant."""
+    variant = "tilt"
+
+    def __init__(self, sim_state: Dict[str, torch.Tensor], cfg: Optional[TaskConfig] = None,
+                 device: str = "cuda:0", fused: bool = True, full_pre_ball_clone: bool = False,
+                 log_stats: bool = False, **kw):
+        cfg = cfg or CONFIGS[self.variant]
+        n = sim_state["root_states"].shape[0]
+        super().__init__(cfg, n, device=device, **kw)
+        if self.device.type != "cuda":
+            raise RuntimeError("the ping-pong task step is CUDA-only (no CPU fallback)")
+        self._lib = N.load()
+        self._task = N.make_task(cfg)
+        self.fused = fused
+        self.log_stats = log_stats
+        dev = self.device
+        # "acquired" PhysX tensors (zero-copy views in the reference, TILT:153-174)
+        self.st: Dict[str, torch.Tensor] = {}
+        for key in _STATE_KEYS:
+            if key in sim_state:
+                self.st[key] = sim_state[key].to(dev).contiguous()
+        self.root_states = self.st["root_states"]
+        self.vec_root_states = self.root_states
+        self.body_states = self.st["rigid_body_states"]
+        self.vec_dof_states = self.st["dof_states"]
+        self.dof_pos = self.vec_dof_states[..., 0]
+        self.dof_vel = self.vec_dof_states[..., 1]
+        self.dof_force_tensor = self.st["dof_forces"]
+        self.ball2_root_states = self.vec_root_states[:, cfg.ball_actor, :]
+        self.initial_vec_root_states = self.st["initial_root_states"]
+        self.initial_dof_states = self.st["initial_dof_states"]
+        self._pd_action_offset = self.st["pd_action_offset"]
+        self._pd_action_scale = self.st["pd_action_scale"]
+        # VecTask buffers may be seeded from the synthetic state (tests do; a fresh task starts at zero)
+        for key in ("progress_buf", "reset_buf"):
+            if key in sim_state:
+                getattr(self, key).copy_(sim_state[key].to(dev))
+        # flag tensors (TILT:241-243, NES:244-248, ALIGN:239, ADOF:279-293)
+        for name, reset_val in zip(cfg.flag_names, cfg.flag_reset_values):
+            t = sim_state[name].to(dev).clone() if name in sim_state else torch.full((n,), reset_val, dtype=torch.bool, device=dev)
+            setattr(self, name, t)
+        for name in cfg.counter_names:
+            t = sim_state[name].to(dev).clone() if name in sim_state else torch.zeros(n, dtype=torch.bool, device=dev)
+            setattr(self, name, t)
+        # saved pre-step ball state: the reference clones the 13-float row (TILT:1020) although only
+        # vx (and vz in ALIGN) is read back; by default only those two floats are kept
+        width = 13 if full_pre_ball_clone else 2
+        self.pre_ball2_root_states = torch.zeros(n, width, device=dev)
+        if "pre_ball_states" in sim_state:
+            src = sim_state["pre_ball_states"].to(dev)
+            self.pre_ball2_root_states.copy_(src if width == 13 else src[:, [7, 9]])
+        self.actions = torch.zeros(n, cfg.num_dofs, device=dev)
+        self.pd_tar = torch.zeros(n, cfg.num_dofs, device=dev)
+        self.stats = EpisodeStats(dev)
+        self._scratch = torch.zeros(16, dtype=torch.int32, device=dev)
+        self._buffers = None
+
+    # -- plumbing -----------------------------------------------------------------------------------
+    def _tensor_dict(self):
+        d = dict(self.st)
+        d.update(obs_buf=self.obs_buf, rew_buf=self.rew_buf, reset_buf=self.reset_buf, progress_buf=self.progress_buf,
+                 pre_ball_states=self.pre_ball2_root_states, actions=self.actions, pd_targets=self.pd_tar,
+                 stats=self.stats.slots, scratch=self._scratch)
+        for name in self.cfg.flag_names + self.cfg.counter_names:
+            d[name] = getattr(self, name)
+        return d
+
+    def buffers(self) -> N.PpkBuffers:
+        if self._buffers is None:
+            self._buffers = N.make_buffers(self.cfg, self._tensor_dict())
+        return self._buffers
+
+    def _stream(self):
+        return N.current_stream_ptr(self.device)
+
+    def _step(self, phases: int):
+        N.check(self._lib.ppk_post_physics_step(self._task, self.buffers(), phases, self._stream()),
+                "ppk_post_physics_step")
+
+    # -- the reference's method set ----------------------------------------------------------------
+    def pre_physics_step(self, actions):
+        """TILT:1002-1020: keep the actions, pd_tar = offset + scale*actions, save the ball state."""
+        self.actions.copy_(actions.to(self.device))
+        N.check(self._lib.ppk_pre_physics_step(self._task, self.buffers(), self._stream()), "ppk_pre_physics_step")
+
+    def compute_reward(self, actions=None):
+        """TILT:739-768 (the statistics the reference prints every `log_every` steps are accumulated
+        on the device instead of `.item()`-ed)."""
+        self._step(N.PHASE_REWARD | (N.PHASE_STATS if self._log_now() else 0))
+
+    def compute_observations(self):
+        self._step(N.PHASE_OBS)
+
+    def reset_idx(self, env_ids, ball_vel=None, ball_pos_yz=None):
+        """TILT:809-906.  `ball_vel` [k,3] are the launch velocities the reference draws with host
+        `random.uniform`; by default rows `env_ids` of the pre-sampled `reset_ball_vel` are used.
+        Returns the int32 (actor_indices, dof_indices) the gym setters take (TILT:876-888)."""
+        env_ids = env_ids.to(self.device, torch.int64).contiguous()
+        k = env_ids.numel()
+        cfg = self.cfg
+        actor_out = torch.empty(k * cfg.num_actors, dtype=torch.int32, device=self.device)
+        dof_per = self.st["dof_indices"].numel() // self.num_envs if "dof_indices" in self.st else 0
+        dof_out = torch.empty(k * max(dof_per, 1), dtype=torch.int32, device=self.device)
+        bv = ball_vel.to(self.device, torch.float32).contiguous() if ball_vel is not None else None
+        byz = ball_pos_yz.to(self.device, torch.float32).contiguous() if ball_pos_yz is not None else None
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        N.check(self._lib.ppk_reset_idx(self._task, self.buffers(), env_ids.data_ptr(), k, ptr(bv), ptr(byz),
+                                        ptr(self.st.get("actor_indices")), ptr(self.st.get("dof_indices")) if dof_per else None,
+                                        dof_per, actor_out.data_ptr(), dof_out.data_ptr() if dof_per else None,
+                                        self._stream()), "ppk_reset_idx")
+        return actor_out, dof_out
+
+    def _log_now(self) -> bool:
+        le = self.cfg.log_every
+        return self.log_stats and le > 0 and self.num_steps % le == 0
+
+    def post_physics_step(self):
+        """TILT:1022-1052.  Fused: one kernel does progress+=1, reward, reset mask, flag updates,
+        the per-env reset and the observations.  With `fused=False` the reference's own sequence of
+        calls is issued (three launches and a host-visible `nonzero`)."""
+        log = self._log_now()
+        if self.fused:
+            self._step(N.PHASE_ALL if log else (N.PHASE_ALL & ~N.PHASE_STATS))
+        elif self.cfg.variant == "base":
+            self._step(N.PHASE_PROGRESS | N.PHASE_RESET)
+            self.compute_observations()
+            self.compute_reward()
+        else:
+            self._step(N.PHASE_PROGRESS)
+            self.compute_reward(self.actions)
+            env_ids = self.reset_buf.nonzero(as_tuple=False).flatten()
+            if len(env_ids) > 0:
+                self.reset_idx(env_ids)
+                for name in self.cfg.counter_names:          # ADOF:1171-1175
+                    getattr(self, name).fill_(0)
+            self.compute_observations()
+        if log:
+            self.stats.reduce(self._lib, self._stream())
+        self.num_steps += 1
+
+
+class HumanoidPingpongBase(PingpongTask):          # tasks/humanoid_pingpong.py:66
+    variant = "base"
+
+
+class HumanoidPingpong(PingpongTask):              # tasks/humanoid_interos_edit_pingpong_only_3_actor.py:58
+    variant = "a3"
+
+
+class HumanoidPingpongTilt(PingpongTask):          # tasks/humanoid_pingpong_3_actor_tilt.py:58
+    variant = "tilt"
+
+
+class HumanoidPingpongTiltNoEarlyStop(PingpongTask):   # tasks/humanoid_pingpong_3_actor_tilt_no_earlystop.py:58
+    variant = "nes"
+
+
+class Humanoid12PingpongTilt(PingpongTask):        # tasks/humanoid_pingpong_4_actor_tilt.py:58
+    variant = "a4"
+
+
+class HumanoidPingpongAlignment(PingpongTask):     # tasks/humanoid_pingpong_alignment.py:58 (class HumanoidPingpongTilt there)
+    variant = "align"
+
+
+class HumanoidPingpongTiltNESSparse27DOF(PingpongTask):   # tasks/humanoid_pingpong_3_actor_all_dof.py:65
+    variant = "adof"
+
+
+# name -> class, as tasks/__init__.py:92-123 maps task names (plus the three it forgets to register)
+isaacgym_task_map = {
+    "HumanoidPingpongBase": HumanoidPingpongBase,
+    "HumanoidPingpongG1": HumanoidPingpong,
+    "HumanoidPingpongTiltG1": HumanoidPingpongTilt,
+    "HumanoidPingpongTiltNoEarlyStopG1": HumanoidPingpongTiltNoEarlyStop,
+    "Humanoid12PingpongTiltG1": Humanoid12PingpongTilt,
+    "HumanoidPingpongAlignmentG1": HumanoidPingpongAlignment,
+    "HumanoidPingpongTiltNESSparse27DOFG1": HumanoidPingpongTiltNESSparse27DOF,
+}
+VARIANT_CLASS = {c.variant: c for c in isaacgym_task_map.values()}
+
+
+def make_task(variant: str, sim_state, **kw) -> PingpongTask:
+    return VARIANT_CLASS[variant](sim_state, **kw)

