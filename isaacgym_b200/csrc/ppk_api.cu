@@ -153,9 +153,9 @@ int ppk_post_physics_step(const PpkTask* t, const PpkBuffers* b, uint32_t phases
   if (rc != PPK_OK) return rc;
   if ((phases & ~((uint32_t)PPK_PHASE_ALL | kPhaseDeferCounterClear)) != 0 || (phases & PPK_PHASE_ALL) == 0)
     return PPK_ERR_VARIANT;
+  if (b->num_envs == 0) return PPK_OK;      // empty shard: nothing to dereference
   rc = check_step_pointers(t, b, phases);
   if (rc != PPK_OK) return rc;
-  if (b->num_envs == 0) return PPK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (t->variant) {
     case PPK_BASE: {

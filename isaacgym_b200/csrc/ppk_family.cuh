@@ -143,7 +143,12 @@ family_step_kernel(const __grid_constant__ KArgs k) {
         int e = f / L::kRbEnv, r = f - e * L::kRbEnv;
         int h = r / (J * kRow), rr = r - h * (J * kRow);
         int j = rr / kRow, c = rr - j * kRow;
-        int id = __shfl_sync(full, (H > 1 && h) ? my_id1 : my_id0, j);
+        // every lane must offer both lists: the source lane's own h says nothing about ours
+        int id = __shfl_sync(full, my_id0, j);
+        if (H > 1) {
+          int id1 = __shfl_sync(full, my_id1, j);
+          if (h) id = id1;
+        }
         v[u] = (e < nvalid) ? ld_stream(g_rb + (size_t)e * env_stride + id * kRow + c) : 0.0f;
       }
 #pragma unroll
