@@ -60,6 +60,20 @@ int fill_args(const PpkTask* t, const PpkBuffers* b, uint32_t phases, KArgs* k) 
   k->die_penalty = t->die_penalty; k->hit_paddle = t->hit_paddle_reward; k->miss_coef = t->miss_paddle_penalty_coefficient;
   k->term_dist = t->is_train ? 0.32f : 1e6f;           // ADOF:1404-1410, is_g1 branch
   k->phases = (int)phases; k->write_flags = t->write_flags; k->reset_dof = t->reset_dof;
+  // Bulk async staging (cp.async.bulk) moves 16-byte aligned windows around each env's rows: legal
+  // when the tensors start 16-byte aligned, ids[1..J) are consecutive rows (one run per env) and a
+  // further row follows ids[0] and ids[J-1] inside the env block (the windows over-read <= 12 bytes).
+  bool bulk = t->num_body_ids >= 2 && b->rigid_body_states && b->root_states && b->dof_states && b->dof_forces;
+  if (bulk) {
+    const void* al[] = {b->rigid_body_states, b->root_states, b->dof_states, b->dof_forces};
+    for (const void* p : al) bulk = bulk && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
+    const int nh = (t->variant == PPK_A4) ? 2 : 1;
+    for (int h = 0; h < nh && bulk; ++h) {
+      for (int j = 2; j < t->num_body_ids; ++j) bulk = bulk && (t->body_ids[h][j] == t->body_ids[h][1] + j - 1);
+      bulk = bulk && (t->body_ids[h][0] + 1 < t->num_bodies) && (t->body_ids[h][t->num_body_ids - 1] + 1 < t->num_bodies);
+    }
+  }
+  k->bulk_ok = bulk ? 1 : 0;
   return PPK_OK;
 }
 
@@ -112,7 +126,7 @@ template <int V, int H, int J, int D, int A, int TILE>
 int launch_family(const KArgs& k, cudaStream_t s) {
   using L = FamilyLayout<H, J, D, A, TILE>;
   auto kern = family_step_kernel<V, H, J, D, A, TILE>;
-  constexpr size_t smem = (size_t)kFamilyWarps * L::kWarpFloats * sizeof(float);
+  constexpr size_t smem = (size_t)L::kFloats * sizeof(float);
   static bool configured = false;        // idempotent attribute; a benign race sets it twice
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -121,9 +135,8 @@ int launch_family(const KArgs& k, cudaStream_t s) {
     }
     configured = true;
   }
-  const long long tiles = (k.n + TILE - 1) / TILE;
-  const long long blocks = (tiles + kFamilyWarps - 1) / kFamilyWarps;
-  kern<<<(unsigned)blocks, kFamilyWarps * 32, smem, s>>>(k);
+  const long long tiles = (k.n + TILE - 1) / TILE;      // one CTA per tile
+  kern<<<(unsigned)tiles, kFamilyThreads, smem, s>>>(k);
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 

@@ -48,6 +48,7 @@ struct KArgs {
   int phases;
   int write_flags;
   int reset_dof;
+  int bulk_ok;   // tensors 16-byte aligned and ids[1..J) consecutive: bulk async staging is legal
 };
 
 __device__ __forceinline__ float warp_sum(float v) {

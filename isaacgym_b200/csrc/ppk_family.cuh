@@ -1,77 +1,186 @@
 // Fused task step for the 3-/4-actor variants (A3, TILT, NES, ALIGN, A4).
 //
-// One warp owns one tile of TILE consecutive envs and runs the whole step for it:
-//   stage   coalesced loads of the tile's rigid-body rows (ids[]), root rows, DOF state and
-//           DOF forces into the warp's shared-memory slice (the state tensors are AoS with
-//           52-byte rows, so per-env vector loads are impossible; lanes walk the flat float
-//           index instead and every 32-byte sector is fetched exactly once);
-//   phase R lane = env: progress+1, reward, die/time-out mask, flag updates, statistics,
-//           predicated reset (root/DOF rows rewritten from the initial tensors), heading frame,
-//           ball in the heading frame; the obs "tail" (dof_pos, 0.1*dof_vel, ball) goes to smem;
-//   phase O lane = (env, body): rotate pos/vel of the J bodies into the heading frame, transpose
-//           inside the warp with shuffles and store each obs row segment contiguously.
-// No block-level synchronisation: warps are independent (only __syncwarp).
+// One CTA of three warps owns one tile of TILE consecutive envs.
+//   stage    The PhysX tensors are AoS with 52-byte rows, so per-env vector loads are impossible.
+//            Instead every env's rigid-body rows ids[1..J) (one contiguous 468-byte run) and row
+//            ids[0] are fetched with 1-D bulk async copies (cp.async.bulk, the TMA engine) of the
+//            enclosing 16-byte-aligned windows (480 B / 64 B), and the tile's slices of the root,
+//            DOF and DOF-force tensors (contiguous across envs) with one bulk copy each.  All
+//            copies complete on one mbarrier; no registers or LSU issue slots are spent on staging
+//            and each 32-byte sector is fetched once.  Tail tiles / misaligned tensors use a plain
+//            LDG path into the same layout.
+//   warp 0   lane = env: progress+1, reward, die/time-out mask, flag updates, statistics, the
+//            predicated reset (root/DOF rows rewritten from the initial tensors), ball in the
+//            heading frame, and the obs "tail" (dof_pos, 0.1*dof_vel, ball).
+//   warps 1,2  lane = (env, body): rotate pos/vel of the J bodies into the heading frame,
+//            transpose inside the warp with shuffles and store obs row segments contiguously.
 #pragma once
+#include "ppk_async.cuh"
 #include "ppk_device.cuh"
 
 namespace ppk {
 
+constexpr int kFamilyThreads = 96;
+
 template <int H, int J, int D, int A, int TILE>
 struct FamilyLayout {
-  static constexpr int kRbEnv = H * J * kRow;          // staged rigid-body floats per env
+  static constexpr int kSpanRows = J - 1;                               // rows ids[1..J)
+  static constexpr int kSpanFloats = ((kSpanRows * kRow + 3 + 3) / 4) * 4;   // 120: run + alignment slack
+  static constexpr int kRow0Floats = 16;                                // 10 used floats + slack
   static constexpr int kRootEnv = A * kRow;
-  static constexpr int kSRb = kRbEnv | 1;              // odd strides: lane = env reads are conflict-free
-  static constexpr int kSRoot = kRootEnv | 1;
-  static constexpr int kSDof = (2 * D) | 1;
-  static constexpr int kSForce = D | 1;
-  static constexpr int kHdr = 5;                       // root pos (3) + heading quat (sz, cw)
   static constexpr int kTail = 2 * D + 6;              // dof_pos, 0.1*dof_vel, ball local pos, vel
   static constexpr int kSTail = kTail | 1;
   static constexpr int kObs = 6 * J + kTail;           // 80 (D=7) / 94 (D=14)
-  static constexpr int kOffRoot = TILE * kSRb;
-  static constexpr int kOffDof = kOffRoot + TILE * kSRoot;
-  static constexpr int kOffForce = kOffDof + TILE * kSDof;
-  static constexpr int kOffHdr = kOffForce + TILE * kSForce;
-  static constexpr int kWarpFloats = kOffHdr + TILE * H * kHdr;
-  // the tail aliases the root/dof/force staging, all of which phase R has consumed by then
-  static_assert(TILE * H * kSTail <= kOffHdr - kOffRoot, "tail does not fit its alias region");
-  static_assert((TILE * kRbEnv) % 32 == 0 && (TILE * kRootEnv) % 32 == 0 && (TILE * 2 * D) % 32 == 0 &&
-                    (TILE * D) % 32 == 0, "flat staging loops assume whole warps");
+  static constexpr int kHdr = 5;                       // root pos (3) + heading quat (sz, cw)
+  // float offsets inside the CTA's shared memory
+  static constexpr int kOffRow0 = TILE * H * kSpanFloats;
+  static constexpr int kOffRoot = kOffRow0 + TILE * H * kRow0Floats;
+  static constexpr int kOffDof = kOffRoot + TILE * kRootEnv;
+  static constexpr int kOffForce = kOffDof + TILE * 2 * D;
+  static constexpr int kOffBar = kOffForce + TILE * D;            // 8-byte mbarrier
+  static constexpr int kOffHdr = kOffBar + 4;
+  static constexpr int kFloats = kOffHdr + 2 * TILE * H * kHdr;   // one heading table per obs warp
+  static constexpr uint32_t kTxBytes =
+      4u * (TILE * H * (kSpanFloats + kRow0Floats) + TILE * kRootEnv + TILE * 2 * D + TILE * D);
+  static_assert((TILE * kRootEnv) % 4 == 0 && (TILE * 2 * D) % 4 == 0 && (TILE * D) % 4 == 0, "16-byte bulk sizes");
+  static_assert(kOffBar % 2 == 0, "mbarrier alignment");
+  static_assert(TILE * H * kSTail <= kOffBar - kOffRoot, "tail does not fit its alias region");
 };
 
-constexpr int kFamilyWarps = 4;   // warps (= tiles) per CTA
-
 template <int V, int H, int J, int D, int A, int TILE>
-__global__ void __launch_bounds__(kFamilyWarps * 32)
+__global__ void __launch_bounds__(kFamilyThreads, 8)
 family_step_kernel(const __grid_constant__ KArgs k) {
   using L = FamilyLayout<H, J, D, A, TILE>;
-  extern __shared__ float smem[];
+  extern __shared__ __align__(128) float smem[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const long long tile = (long long)blockIdx.x * kFamilyWarps + warp;
-  const long long env0 = tile * TILE;
-  if (env0 >= k.n) return;
+  const long long env0 = (long long)blockIdx.x * TILE;
   const int nvalid = (int)min((long long)TILE, k.n - env0);
 
-  float* rb_s = smem + (size_t)warp * L::kWarpFloats;
-  float* root_s = rb_s + L::kOffRoot;
-  float* dof_s = rb_s + L::kOffDof;
-  float* force_s = rb_s + L::kOffForce;
-  float* hdr_s = rb_s + L::kOffHdr;
+  float* span_s = smem;
+  float* row0_s = smem + L::kOffRow0;
+  float* root_s = smem + L::kOffRoot;
+  float* dof_s = smem + L::kOffDof;
+  float* force_s = smem + L::kOffForce;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   float* tail_s = root_s;
 
   const int phases = k.phases;
-  const bool lane_env = lane < nvalid;          // this lane owns env0 + lane in the lane = env phases
-  const long long env = env0 + lane;
+  const bool bulk = k.bulk_ok && (nvalid == TILE);
+  const int env_stride = k.B * kRow;
+  const float* g_rb = k.rb + (size_t)env0 * env_stride;
 
-  // ---- per-env scalars straight from global (already one value per env) ----------------------
-  long long prog = 0;
-  long long reset_prev = 0;
+  // position of an env's run / row inside its 16-byte aligned staging window
+  auto span_off = [&](int e, int h) -> int {
+    if (!bulk) return 0;
+    return (int)((reinterpret_cast<uintptr_t>(g_rb + (size_t)e * env_stride + k.ids[h][1] * kRow) & 15u) >> 2);
+  };
+  auto row0_off = [&](int e, int h) -> int {
+    if (!bulk) return 0;
+    return (int)((reinterpret_cast<uintptr_t>(g_rb + (size_t)e * env_stride + k.ids[h][0] * kRow) & 15u) >> 2);
+  };
+
+  // ---- stage ---------------------------------------------------------------------------------------
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar, L::kTxBytes);
+        bulk_g2s(root_s, k.root + (size_t)env0 * L::kRootEnv, 4u * TILE * L::kRootEnv, bar);
+        bulk_g2s(dof_s, k.dof + (size_t)env0 * 2 * D, 4u * TILE * 2 * D, bar);
+        bulk_g2s(force_s, k.force + (size_t)env0 * D, 4u * TILE * D, bar);
+      }
+      __syncwarp();
+      for (int u = lane; u < TILE * H; u += 32) {       // one (env, humanoid) pair per lane
+        const int e = u / H, h = u - e * H;
+        const float* row = g_rb + (size_t)e * env_stride;
+        const uintptr_t a1 = reinterpret_cast<uintptr_t>(row + k.ids[h][1] * kRow) & ~(uintptr_t)15;
+        const uintptr_t a0 = reinterpret_cast<uintptr_t>(row + k.ids[h][0] * kRow) & ~(uintptr_t)15;
+        bulk_g2s(span_s + u * L::kSpanFloats, reinterpret_cast<const void*>(a1), 4u * L::kSpanFloats, bar);
+        bulk_g2s(row0_s + u * L::kRow0Floats, reinterpret_cast<const void*>(a0), 4u * L::kRow0Floats, bar);
+      }
+    }
+  } else {
+    // generic path (tail tile, unaligned tensors, non-consecutive ids): plain loads, same layout
+    for (int f = threadIdx.x; f < TILE * H * J * kRow; f += kFamilyThreads) {
+      const int u = f / (J * kRow), r = f - u * (J * kRow);
+      const int e = u / H, h = u - e * H;
+      const int j = r / kRow, c = r - j * kRow;
+      float v = (e < nvalid) ? g_rb[(size_t)e * env_stride + k.ids[h][j] * kRow + c] : 0.0f;
+      if (j == 0) row0_s[u * L::kRow0Floats + c] = v;
+      else span_s[u * L::kSpanFloats + (j - 1) * kRow + c] = v;
+    }
+    for (int f = threadIdx.x; f < TILE * L::kRootEnv; f += kFamilyThreads)
+      root_s[f] = (f < nvalid * L::kRootEnv) ? k.root[(size_t)env0 * L::kRootEnv + f] : 0.0f;
+    for (int f = threadIdx.x; f < TILE * 2 * D; f += kFamilyThreads)
+      dof_s[f] = (f < nvalid * 2 * D) ? k.dof[(size_t)env0 * 2 * D + f] : 0.0f;
+    for (int f = threadIdx.x; f < TILE * D; f += kFamilyThreads)
+      force_s[f] = (f < nvalid * D) ? k.force[(size_t)env0 * D + f] : 0.0f;
+    __syncthreads();
+  }
+
+  if (warp != 0) {
+    // ================= warps 1, 2: body observations =============================================
+    if (!(phases & PPK_PHASE_OBS)) return;
+    if (bulk) mbar_wait(bar, 0);
+    float* hdr_s = smem + L::kOffHdr + (warp - 1) * (TILE * H * L::kHdr);
+    // heading frames, lane = (env, humanoid)
+    for (int u = lane; u < TILE * H; u += 32) {
+      const int e = u / H, h = u - e * H;
+      const float* r0 = row0_s + u * L::kRow0Floats + row0_off(e, h);
+      Heading hq = heading_quat_inv(r0[3], r0[4], r0[5], r0[6]);
+      float* hd = hdr_s + u * L::kHdr;
+      hd[0] = r0[0]; hd[1] = r0[1]; hd[2] = r0[2]; hd[3] = hq.sz; hd[4] = hq.cw;
+    }
+    __syncwarp();
+    constexpr int P = 32 / J;                       // envs per pass
+    constexpr int kPasses = (TILE + P - 1) / P;
+    const int a = lane / J, t = lane - a * J;
+    const bool lane_on = a < P;
+    float* g_obs = k.obs + (size_t)env0 * H * L::kObs;
+#pragma unroll 1
+    for (int unit = warp - 1; unit < kPasses * H; unit += 2) {
+      const int pass = unit / H, h = unit - pass * H;
+      const int e = pass * P + a;
+      const bool ok = lane_on && (e < nvalid);
+      const int u = (ok ? e : 0) * H + h;
+      const float* hd = hdr_s + u * L::kHdr;
+      Heading hq; hq.sz = hd[3]; hq.cw = hd[4];
+      const int tt = lane_on ? t : 0;
+      const float* row = (tt == 0) ? (row0_s + u * L::kRow0Floats + row0_off(ok ? e : 0, h))
+                                   : (span_s + u * L::kSpanFloats + span_off(ok ? e : 0, h) + (tt - 1) * kRow);
+      float lp[3], lv[3];
+      rotate_heading(hq, row[0] - hd[0], row[1] - hd[1], row[2] - hd[2], lp[0], lp[1], lp[2]);
+      rotate_heading(hq, row[7], row[8], row[9], lv[0], lv[1], lv[2]);
+      float* orow = g_obs + ((size_t)e * H + h) * L::kObs;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        // output position o = t + i*J of this env's 3J-float segment comes from body o/3, component o%3
+        const int o = tt + i * J;
+        const int src = (lane_on ? a * J : 0) + o / 3, comp = o - (o / 3) * 3;
+        float x = __shfl_sync(full, lp[0], src), y = __shfl_sync(full, lp[1], src), z = __shfl_sync(full, lp[2], src);
+        float pv = comp == 0 ? x : (comp == 1 ? y : z);
+        x = __shfl_sync(full, lv[0], src); y = __shfl_sync(full, lv[1], src); z = __shfl_sync(full, lv[2], src);
+        float vv = comp == 0 ? x : (comp == 1 ? y : z);
+        if (ok) { st_stream(orow + o, pv); st_stream(orow + 3 * J + o, vv); }
+      }
+    }
+    return;
+  }
+
+  // ================= warp 0: reward / reset / tail, lane = env ==========================================
+  const bool lane_env = lane < nvalid;
+  const long long env = env0 + lane;
+  long long prog = 0, reset_prev = 0;
   float pre_vx = 0.0f, pre_vz = 0.0f;
   constexpr int NF = (V == PPK_TILT) ? 3 : (V == PPK_A4) ? 6 : (V == PPK_NES) ? 2 : (V == PPK_ALIGN) ? 1 : 0;
   bool flag[NF > 0 ? NF : 1];
-  if (lane_env) {
+  if (lane_env) {       // per-env scalars come straight from global and overlap the bulk copies
     prog = k.progress[env];
     if (!(phases & PPK_PHASE_REWARD)) reset_prev = k.reset[env];
     if (phases & PPK_PHASE_REWARD) {
@@ -82,94 +191,24 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       for (int i = 0; i < NF; ++i) flag[i] = k.flags[i][env] != 0;
     }
   }
+  if (bulk) mbar_wait(bar, 0);
 
-  // ---- stage the tile --------------------------------------------------------------------------
-  {
-    // root / dof / force: the tile's slice of each tensor is one contiguous run
-    constexpr int kRootIt = TILE * L::kRootEnv / 32, kDofIt = TILE * 2 * D / 32, kForceIt = TILE * D / 32;
-    const float* g_root = k.root + (size_t)env0 * L::kRootEnv;
-    const float* g_dof = k.dof + (size_t)env0 * 2 * D;
-    const float* g_force = k.force + (size_t)env0 * D;
-    float v[kRootIt + kDofIt + kForceIt];
-#pragma unroll
-    for (int i = 0; i < kRootIt; ++i) {
-      int f = i * 32 + lane;
-      v[i] = (f < nvalid * L::kRootEnv) ? ld_stream(g_root + f) : 0.0f;
-    }
-#pragma unroll
-    for (int i = 0; i < kDofIt; ++i) {
-      int f = i * 32 + lane;
-      v[kRootIt + i] = (f < nvalid * 2 * D) ? ld_stream(g_dof + f) : 0.0f;
-    }
-#pragma unroll
-    for (int i = 0; i < kForceIt; ++i) {
-      int f = i * 32 + lane;
-      v[kRootIt + kDofIt + i] = (f < nvalid * D) ? ld_stream(g_force + f) : 0.0f;
-    }
-#pragma unroll
-    for (int i = 0; i < kRootIt; ++i) {
-      int f = i * 32 + lane;
-      int e = f / L::kRootEnv, r = f - e * L::kRootEnv;
-      root_s[e * L::kSRoot + r] = v[i];
-    }
-#pragma unroll
-    for (int i = 0; i < kDofIt; ++i) {
-      int f = i * 32 + lane;
-      int e = f / (2 * D), r = f - e * (2 * D);
-      dof_s[e * L::kSDof + r] = v[kRootIt + i];
-    }
-#pragma unroll
-    for (int i = 0; i < kForceIt; ++i) {
-      int f = i * 32 + lane;
-      int e = f / D, r = f - e * D;
-      force_s[e * L::kSForce + r] = v[kRootIt + kDofIt + i];
-    }
-  }
-  {
-    // rigid-body rows ids[h][0..J): lanes walk the flat (env, humanoid, body, column) index, so
-    // consecutive ids (31..39) give consecutive addresses and fully coalesced requests
-    constexpr int kIt = TILE * L::kRbEnv / 32;    // 130
-    constexpr int kBatch = (kIt % 65 == 0) ? 65 : (kIt % 26 == 0) ? 26 : (kIt % 13 == 0 ? 13 : 1);
-    const int my_id0 = (lane < J) ? k.ids[0][lane] : 0;
-    const int my_id1 = (H > 1 && lane < J) ? k.ids[1][lane] : 0;
-    const float* g_rb = k.rb + (size_t)env0 * k.B * kRow;
-    const int env_stride = k.B * kRow;
-#pragma unroll 1
-    for (int it0 = 0; it0 < kIt; it0 += kBatch) {
-      float v[kBatch];
-#pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        int f = (it0 + u) * 32 + lane;
-        int e = f / L::kRbEnv, r = f - e * L::kRbEnv;
-        int h = r / (J * kRow), rr = r - h * (J * kRow);
-        int j = rr / kRow, c = rr - j * kRow;
-        // every lane must offer both lists: the source lane's own h says nothing about ours
-        int id = __shfl_sync(full, my_id0, j);
-        if (H > 1) {
-          int id1 = __shfl_sync(full, my_id1, j);
-          if (h) id = id1;
-        }
-        v[u] = (e < nvalid) ? ld_stream(g_rb + (size_t)e * env_stride + id * kRow + c) : 0.0f;
-      }
-#pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        int f = (it0 + u) * 32 + lane;
-        int e = f / L::kRbEnv, r = f - e * L::kRbEnv;
-        rb_s[e * L::kSRb + r] = v[u];
-      }
-    }
-  }
-  __syncwarp();
-
-  // ---- phase R: lane = env ---------------------------------------------------------------------
   const int le = (lane < TILE) ? lane : 0;     // smem row this lane reads (idle lanes read row 0)
-  const float* my_root = root_s + le * L::kSRoot;
+  const float* my_root = root_s + le * L::kRootEnv;
   const float* ball = my_root + k.ball * kRow;
   float bx = ball[0], by = ball[1], bz = ball[2];
   float bvx = ball[7], bvy = ball[8], bvz = ball[9];
+  float hx[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) hx[h] = my_root[k.hum[h] * kRow];
   float dofv[2 * D];
 #pragma unroll
-  for (int i = 0; i < 2 * D; ++i) dofv[i] = dof_s[le * L::kSDof + i];
+  for (int i = 0; i < 2 * D; ++i) dofv[i] = dof_s[le * 2 * D + i];
+  float power = 0.0f;
+  if (phases & PPK_PHASE_REWARD) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) power += fabsf(force_s[le * D + d] * dofv[2 * d + 1]);
+  }
 
   long long p_new = prog + ((phases & PPK_PHASE_PROGRESS) ? 1 : 0);
   bool is_reset = reset_prev != 0;
@@ -178,23 +217,19 @@ family_step_kernel(const __grid_constant__ KArgs k) {
   for (int h = 0; h < H; ++h) rew[h] = 0.0f;
 
   if (phases & PPK_PHASE_REWARD) {
-    float power = 0.0f;
-#pragma unroll
-    for (int d = 0; d < D; ++d) power += fabsf(force_s[le * L::kSForce + d] * dofv[2 * d + 1]);
     bool die = false;
 #pragma unroll
     for (int h = 0; h < H; ++h) {
       Scene s;
       s.bx = bx; s.by = by; s.bz = bz; s.vx = bvx; s.vz = bvz;
       s.pre_vx = pre_vx; s.pre_vz = pre_vz;
-      if (k.paddle_j[h] >= 0) {
-        const float* pd = rb_s + le * L::kSRb + (h * J + k.paddle_j[h]) * kRow;
-        s.px = pd[0]; s.py = pd[1]; s.pz = pd[2];
-      } else {
-        const float* pd = k.rb + ((size_t)(lane_env ? env : env0) * k.B + k.paddle_body[h]) * kRow;
-        s.px = pd[0]; s.py = pd[1]; s.pz = pd[2];
-      }
-      s.hx = my_root[k.hum[h] * kRow];
+      const int pj = k.paddle_j[h];
+      const float* pd;
+      if (pj == 0) pd = row0_s + (le * H + h) * L::kRow0Floats + row0_off(le, h);
+      else if (pj > 0) pd = span_s + (le * H + h) * L::kSpanFloats + span_off(le, h) + (pj - 1) * kRow;
+      else pd = k.rb + ((size_t)(lane_env ? env : env0) * k.B + k.paddle_body[h]) * kRow;
+      s.px = pd[0]; s.py = pd[1]; s.pz = pd[2];
+      s.hx = hx[h];
       s.power_reward = (-k.power_coef) * power;
       s.progress = p_new;
       bool d = false;
@@ -217,12 +252,11 @@ family_step_kernel(const __grid_constant__ KArgs k) {
   }
 
   if (phases & PPK_PHASE_STATS) {
-    double s_rew = lane_env ? (double)rew[0] : 0.0;
-    double s_prog = lane_env ? (double)p_new : 0.0;
-    double s_rst = (lane_env && is_reset) ? 1.0 : 0.0;
-    s_rew = warp_sum(s_rew); s_prog = warp_sum(s_prog); s_rst = warp_sum(s_rst);
+    double s_rew = warp_sum(lane_env ? (double)rew[0] : 0.0);
+    double s_prog = warp_sum(lane_env ? (double)p_new : 0.0);
+    double s_rst = warp_sum((lane_env && is_reset) ? 1.0 : 0.0);
     if (lane == 0) {
-      double* slot = k.stats + (size_t)(tile % PPK_STATS_SLOTS) * PPK_NUM_STATS;
+      double* slot = k.stats + (size_t)(blockIdx.x % PPK_STATS_SLOTS) * PPK_NUM_STATS;
       atomicAdd(slot + PPK_STAT_REWARD, s_rew);
       atomicAdd(slot + PPK_STAT_PROGRESS, s_prog);
       atomicAdd(slot + PPK_STAT_RESETS, s_rst);
@@ -266,24 +300,18 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       }
     }
   }
-
   if (!(phases & PPK_PHASE_OBS)) return;
 
-  // ---- heading frame + ball in the frame; tail of the obs row goes through smem ------------------
+  // ---- ball in the heading frame; tail of the obs row goes through smem -----------------------------
   float tail_ball[H][6];
 #pragma unroll
   for (int h = 0; h < H; ++h) {
-    const float* r0 = rb_s + le * L::kSRb + h * J * kRow;   // body ids[h][0]: the heading / root body
-    float rx = r0[0], ry = r0[1], rz = r0[2];
+    const float* r0 = row0_s + (le * H + h) * L::kRow0Floats + row0_off(le, h);
     Heading hq = heading_quat_inv(r0[3], r0[4], r0[5], r0[6]);
-    if (lane < TILE) {
-      float* hd = hdr_s + (le * H + h) * L::kHdr;
-      hd[0] = rx; hd[1] = ry; hd[2] = rz; hd[3] = hq.sz; hd[4] = hq.cw;
-    }
-    rotate_heading(hq, bx - rx, by - ry, bz - rz, tail_ball[h][0], tail_ball[h][1], tail_ball[h][2]);
+    rotate_heading(hq, bx - r0[0], by - r0[1], bz - r0[2], tail_ball[h][0], tail_ball[h][1], tail_ball[h][2]);
     rotate_heading(hq, bvx, bvy, bvz, tail_ball[h][3], tail_ball[h][4], tail_ball[h][5]);
   }
-  __syncwarp();   // every lane is done with root_s / dof_s / force_s: the tail may overwrite them
+  __syncwarp();   // every lane of this warp is done with root_s / dof_s / force_s (only warp 0 reads them)
   if (lane < TILE) {
 #pragma unroll
     for (int h = 0; h < H; ++h) {
@@ -295,39 +323,8 @@ family_step_kernel(const __grid_constant__ KArgs k) {
     }
   }
   __syncwarp();
-
-  // ---- phase O: lane = (env a of the pass, body t) ---------------------------------------------
-  constexpr int P = 32 / J;                       // envs per pass
-  const int a = lane / J, t = lane - a * J;
-  float* g_obs = k.obs + (size_t)env0 * H * L::kObs;
-#pragma unroll 1
-  for (int pass = 0; pass * P < TILE; ++pass) {
-    const int e = pass * P + a;
-    const bool ok = (a < P) && (e < nvalid);
-    const int ec = ok ? e : 0;
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-      const float* hd = hdr_s + (ec * H + h) * L::kHdr;
-      Heading hq; hq.sz = hd[3]; hq.cw = hd[4];
-      const float* row = rb_s + ec * L::kSRb + (h * J + (a < P ? t : 0)) * kRow;
-      float lp[3], lv[3];
-      rotate_heading(hq, row[0] - hd[0], row[1] - hd[1], row[2] - hd[2], lp[0], lp[1], lp[2]);
-      rotate_heading(hq, row[7], row[8], row[9], lv[0], lv[1], lv[2]);
-      float* orow = g_obs + ((size_t)e * H + h) * L::kObs;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        // output position o = t + i*J of this env's 3J-float segment comes from body o/3, component o%3
-        const int o = t + i * J;
-        const int src = (a < P ? a * J : 0) + o / 3, comp = o - (o / 3) * 3;
-        float x = __shfl_sync(full, lp[0], src), y = __shfl_sync(full, lp[1], src), z = __shfl_sync(full, lp[2], src);
-        float pv = comp == 0 ? x : (comp == 1 ? y : z);
-        x = __shfl_sync(full, lv[0], src); y = __shfl_sync(full, lv[1], src); z = __shfl_sync(full, lv[2], src);
-        float vv = comp == 0 ? x : (comp == 1 ? y : z);
-        if (ok) { st_stream(orow + o, pv); st_stream(orow + 3 * J + o, vv); }
-      }
-    }
-  }
   // tail: dof_pos, 0.1*dof_vel, ball local pos/vel -- kTail contiguous floats per (env, humanoid)
+  float* g_obs = k.obs + (size_t)env0 * H * L::kObs;
   constexpr int kTailIt = (TILE * H * L::kTail + 31) / 32;
 #pragma unroll 4
   for (int i = 0; i < kTailIt; ++i) {
