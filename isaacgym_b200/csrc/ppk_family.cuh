@@ -4,16 +4,18 @@
 //   stage    The PhysX tensors are AoS with 52-byte rows, so per-env vector loads are impossible.
 //            Instead every env's rigid-body rows ids[1..J) (one contiguous 468-byte run) and row
 //            ids[0] are fetched with 1-D bulk async copies (cp.async.bulk, the TMA engine) of the
-//            enclosing 16-byte-aligned windows (480 B / 64 B), and the tile's slices of the root,
-//            DOF and DOF-force tensors (contiguous across envs) with one bulk copy each.  All
-//            copies complete on one mbarrier; no registers or LSU issue slots are spent on staging
-//            and each 32-byte sector is fetched once.  Tail tiles / misaligned tensors use a plain
-//            LDG path into the same layout.
+//            enclosing 16-byte-aligned windows (480 B / 64 B), and the tile's slices of the DOF
+//            and DOF-force tensors (contiguous across envs) with one bulk copy each.  All copies
+//            complete on one mbarrier; no registers or LSU issue slots are spent on staging.  The
+//            few per-env scalars (progress, flags, saved ball velocity, ball / humanoid root
+//            fields) are plain loads issued before the wait.  Tail tiles / misaligned tensors
+//            use an LDG path into the same layout.
 //   warp 0   lane = env: progress+1, reward, die/time-out mask, flag updates, statistics, the
 //            predicated reset (root/DOF rows rewritten from the initial tensors), ball in the
 //            heading frame, and the obs "tail" (dof_pos, 0.1*dof_vel, ball).
-//   warps 1,2  lane = (env, body): rotate pos/vel of the J bodies into the heading frame,
-//            transpose inside the warp with shuffles and store obs row segments contiguously.
+//   warps 1,2  heading frames of their half of the (env, humanoid) units, then lane = output
+//            float: every lane produces one component of a rotated body position and velocity,
+//            so each obs row segment is stored as one contiguous 120-byte run.
 #pragma once
 #include "ppk_async.cuh"
 #include "ppk_device.cuh"
@@ -24,35 +26,38 @@ constexpr int kFamilyThreads = 96;
 
 template <int H, int J, int D, int A, int TILE>
 struct FamilyLayout {
+  static constexpr int kUnits = TILE * H;                               // (env, humanoid) pairs
   static constexpr int kSpanRows = J - 1;                               // rows ids[1..J)
   static constexpr int kSpanFloats = ((kSpanRows * kRow + 3 + 3) / 4) * 4;   // 120: run + alignment slack
   static constexpr int kRow0Floats = 16;                                // 10 used floats + slack
   static constexpr int kRootEnv = A * kRow;
   static constexpr int kTail = 2 * D + 6;              // dof_pos, 0.1*dof_vel, ball local pos, vel
-  static constexpr int kSTail = kTail | 1;
   static constexpr int kObs = 6 * J + kTail;           // 80 (D=7) / 94 (D=14)
-  static constexpr int kHdr = 5;                       // root pos (3) + heading quat (sz, cw)
+  static constexpr int kHdr = 8;                       // a0, sz, cw, root pos (3), window offsets (2)
   // float offsets inside the CTA's shared memory
-  static constexpr int kOffRow0 = TILE * H * kSpanFloats;
-  static constexpr int kOffRoot = kOffRow0 + TILE * H * kRow0Floats;
-  static constexpr int kOffDof = kOffRoot + TILE * kRootEnv;
+  static constexpr int kOffRow0 = kUnits * kSpanFloats;
+  static constexpr int kOffDof = kOffRow0 + kUnits * kRow0Floats;
   static constexpr int kOffForce = kOffDof + TILE * 2 * D;
-  static constexpr int kOffBar = kOffForce + TILE * D;            // 8-byte mbarrier
-  static constexpr int kOffHdr = kOffBar + 4;
-  static constexpr int kFloats = kOffHdr + 2 * TILE * H * kHdr;   // one heading table per obs warp
-  static constexpr uint32_t kTxBytes =
-      4u * (TILE * H * (kSpanFloats + kRow0Floats) + TILE * kRootEnv + TILE * 2 * D + TILE * D);
-  static_assert((TILE * kRootEnv) % 4 == 0 && (TILE * 2 * D) % 4 == 0 && (TILE * D) % 4 == 0, "16-byte bulk sizes");
+  static constexpr int kOffHdr = kOffForce + TILE * D;
+  static constexpr int kOffBar = kOffHdr + kUnits * kHdr;            // 8-byte mbarrier
+  static constexpr int kFloats = kOffBar + 4;
+  static constexpr uint32_t kTxBytes = 4u * (kUnits * (kSpanFloats + kRow0Floats) + TILE * 2 * D + TILE * D);
+  static_assert((TILE * 2 * D) % 4 == 0 && (TILE * D) % 4 == 0, "16-byte bulk sizes");
   static_assert(kOffBar % 2 == 0, "mbarrier alignment");
-  static_assert(TILE * H * kSTail <= kOffBar - kOffRoot, "tail does not fit its alias region");
+  static_assert(3 * J <= 32, "one lane per output float of a body segment");
+  static_assert(kUnits % 2 == 0 && kUnits / 2 <= 32, "two obs warps, one heading per lane");
+  static_assert(H * 6 <= D, "ball-in-frame scratch aliases the force staging");
 };
 
+// named barrier 1: obs warps arrive once their heading tables are written, warp 0 waits on it
+__device__ __forceinline__ void hdr_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(kFamilyThreads) : "memory"); }
+__device__ __forceinline__ void hdr_wait() { asm volatile("bar.sync 1, %0;" ::"n"(kFamilyThreads) : "memory"); }
+
 template <int V, int H, int J, int D, int A, int TILE>
-__global__ void __launch_bounds__(kFamilyThreads, 8)
+__global__ void __launch_bounds__(kFamilyThreads, 10)
 family_step_kernel(const __grid_constant__ KArgs k) {
   using L = FamilyLayout<H, J, D, A, TILE>;
   extern __shared__ __align__(128) float smem[];
-  const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long env0 = (long long)blockIdx.x * TILE;
@@ -60,26 +65,16 @@ family_step_kernel(const __grid_constant__ KArgs k) {
 
   float* span_s = smem;
   float* row0_s = smem + L::kOffRow0;
-  float* root_s = smem + L::kOffRoot;
   float* dof_s = smem + L::kOffDof;
   float* force_s = smem + L::kOffForce;
+  float* hdr_s = smem + L::kOffHdr;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
-  float* tail_s = root_s;
+  float* ball_s = force_s;          // [unit][6], written by warp 0 after it consumed the forces
 
   const int phases = k.phases;
   const bool bulk = k.bulk_ok && (nvalid == TILE);
   const int env_stride = k.B * kRow;
   const float* g_rb = k.rb + (size_t)env0 * env_stride;
-
-  // position of an env's run / row inside its 16-byte aligned staging window
-  auto span_off = [&](int e, int h) -> int {
-    if (!bulk) return 0;
-    return (int)((reinterpret_cast<uintptr_t>(g_rb + (size_t)e * env_stride + k.ids[h][1] * kRow) & 15u) >> 2);
-  };
-  auto row0_off = [&](int e, int h) -> int {
-    if (!bulk) return 0;
-    return (int)((reinterpret_cast<uintptr_t>(g_rb + (size_t)e * env_stride + k.ids[h][0] * kRow) & 15u) >> 2);
-  };
 
   // ---- stage ---------------------------------------------------------------------------------------
   if (bulk) {
@@ -88,26 +83,24 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       mbar_fence_init();
     }
     __syncthreads();
-    if (warp == 0) {
-      if (lane == 0) {
-        mbar_arrive_expect_tx(bar, L::kTxBytes);
-        bulk_g2s(root_s, k.root + (size_t)env0 * L::kRootEnv, 4u * TILE * L::kRootEnv, bar);
-        bulk_g2s(dof_s, k.dof + (size_t)env0 * 2 * D, 4u * TILE * 2 * D, bar);
-        bulk_g2s(force_s, k.force + (size_t)env0 * D, 4u * TILE * D, bar);
-      }
-      __syncwarp();
-      for (int u = lane; u < TILE * H; u += 32) {       // one (env, humanoid) pair per lane
-        const int e = u / H, h = u - e * H;
-        const float* row = g_rb + (size_t)e * env_stride;
-        const uintptr_t a1 = reinterpret_cast<uintptr_t>(row + k.ids[h][1] * kRow) & ~(uintptr_t)15;
-        const uintptr_t a0 = reinterpret_cast<uintptr_t>(row + k.ids[h][0] * kRow) & ~(uintptr_t)15;
-        bulk_g2s(span_s + u * L::kSpanFloats, reinterpret_cast<const void*>(a1), 4u * L::kSpanFloats, bar);
-        bulk_g2s(row0_s + u * L::kRow0Floats, reinterpret_cast<const void*>(a0), 4u * L::kRow0Floats, bar);
-      }
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(bar, L::kTxBytes);
+      bulk_g2s(dof_s, k.dof + (size_t)env0 * 2 * D, 4u * TILE * 2 * D, bar);
+      bulk_g2s(force_s, k.force + (size_t)env0 * D, 4u * TILE * D, bar);
+    }
+    // the 2 x kUnits row windows are issued by all three warps (the copy instruction takes
+    // warp-uniform operands, so each warp serialises over its lanes)
+    for (int u = warp + 3 * lane; u < L::kUnits; u += 96) {
+      const int e = u / H, h = u - e * H;
+      const float* row = g_rb + (size_t)e * env_stride;
+      const uintptr_t a1 = reinterpret_cast<uintptr_t>(row + k.ids[h][1] * kRow) & ~(uintptr_t)15;
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(row + k.ids[h][0] * kRow) & ~(uintptr_t)15;
+      bulk_g2s(span_s + u * L::kSpanFloats, reinterpret_cast<const void*>(a1), 4u * L::kSpanFloats, bar);
+      bulk_g2s(row0_s + u * L::kRow0Floats, reinterpret_cast<const void*>(a0), 4u * L::kRow0Floats, bar);
     }
   } else {
     // generic path (tail tile, unaligned tensors, non-consecutive ids): plain loads, same layout
-    for (int f = threadIdx.x; f < TILE * H * J * kRow; f += kFamilyThreads) {
+    for (int f = threadIdx.x; f < L::kUnits * J * kRow; f += kFamilyThreads) {
       const int u = f / (J * kRow), r = f - u * (J * kRow);
       const int e = u / H, h = u - e * H;
       const int j = r / kRow, c = r - j * kRow;
@@ -115,8 +108,6 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       if (j == 0) row0_s[u * L::kRow0Floats + c] = v;
       else span_s[u * L::kSpanFloats + (j - 1) * kRow + c] = v;
     }
-    for (int f = threadIdx.x; f < TILE * L::kRootEnv; f += kFamilyThreads)
-      root_s[f] = (f < nvalid * L::kRootEnv) ? k.root[(size_t)env0 * L::kRootEnv + f] : 0.0f;
     for (int f = threadIdx.x; f < TILE * 2 * D; f += kFamilyThreads)
       dof_s[f] = (f < nvalid * 2 * D) ? k.dof[(size_t)env0 * 2 * D + f] : 0.0f;
     for (int f = threadIdx.x; f < TILE * D; f += kFamilyThreads)
@@ -128,46 +119,50 @@ family_step_kernel(const __grid_constant__ KArgs k) {
     // ================= warps 1, 2: body observations =============================================
     if (!(phases & PPK_PHASE_OBS)) return;
     if (bulk) mbar_wait(bar, 0);
-    float* hdr_s = smem + L::kOffHdr + (warp - 1) * (TILE * H * L::kHdr);
-    // heading frames, lane = (env, humanoid)
-    for (int u = lane; u < TILE * H; u += 32) {
+    // heading frames of this warp's units u = 2*lane + (warp-1)
+    if (lane < L::kUnits / 2) {
+      const int u = 2 * lane + (warp - 1);
       const int e = u / H, h = u - e * H;
-      const float* r0 = row0_s + u * L::kRow0Floats + row0_off(e, h);
+      int off0 = 0, off1 = 0;
+      if (bulk) {   // where the row sits inside its 16-byte aligned staging window
+        const float* row = g_rb + (size_t)e * env_stride;
+        off0 = (int)((reinterpret_cast<uintptr_t>(row + k.ids[h][0] * kRow) & 15u) >> 2);
+        off1 = (int)((reinterpret_cast<uintptr_t>(row + k.ids[h][1] * kRow) & 15u) >> 2);
+      }
+      const float* r0 = row0_s + u * L::kRow0Floats + off0;
       Heading hq = heading_quat_inv(r0[3], r0[4], r0[5], r0[6]);
       float* hd = hdr_s + u * L::kHdr;
-      hd[0] = r0[0]; hd[1] = r0[1]; hd[2] = r0[2]; hd[3] = hq.sz; hd[4] = hq.cw;
+      hd[0] = 2.0f * (hq.cw * hq.cw) - 1.0f;
+      hd[1] = hq.sz; hd[2] = hq.cw;
+      hd[3] = r0[0]; hd[4] = r0[1]; hd[5] = r0[2];
+      hd[6] = __int_as_float(off0); hd[7] = __int_as_float(off1);
     }
+    hdr_arrive();       // warp 0 needs the frames for the ball
     __syncwarp();
-    constexpr int P = 32 / J;                       // envs per pass
-    constexpr int kPasses = (TILE + P - 1) / P;
-    const int a = lane / J, t = lane - a * J;
-    const bool lane_on = a < P;
+    // lane = output float o of a 3J-float segment: body j = o/3, component c = o%3.
+    //   out_c = v_c*a0 + ((s1*v_o)*m)*2 with (s1, o, m) = (-sz, y, cw) / (sz, x, cw) / (sz, z, sz)
+    // which is my_quat_rotate((0,0,sz,cw), v) component by component, same operation order.
+    const bool lane_on = lane < 3 * J;
+    const int o = lane_on ? lane : 0;
+    const int j = o / 3, c = o - j * 3;
+    const int oth = (c == 0) ? 1 : (c == 1 ? 0 : 2);
+    const float sgn = (c == 0) ? -1.0f : 1.0f;
     float* g_obs = k.obs + (size_t)env0 * H * L::kObs;
-#pragma unroll 1
-    for (int unit = warp - 1; unit < kPasses * H; unit += 2) {
-      const int pass = unit / H, h = unit - pass * H;
-      const int e = pass * P + a;
-      const bool ok = lane_on && (e < nvalid);
-      const int u = (ok ? e : 0) * H + h;
+#pragma unroll 2
+    for (int u = warp - 1; u < L::kUnits; u += 2) {
+      const int e = u / H;
       const float* hd = hdr_s + u * L::kHdr;
-      Heading hq; hq.sz = hd[3]; hq.cw = hd[4];
-      const int tt = lane_on ? t : 0;
-      const float* row = (tt == 0) ? (row0_s + u * L::kRow0Floats + row0_off(ok ? e : 0, h))
-                                   : (span_s + u * L::kSpanFloats + span_off(ok ? e : 0, h) + (tt - 1) * kRow);
-      float lp[3], lv[3];
-      rotate_heading(hq, row[0] - hd[0], row[1] - hd[1], row[2] - hd[2], lp[0], lp[1], lp[2]);
-      rotate_heading(hq, row[7], row[8], row[9], lv[0], lv[1], lv[2]);
-      float* orow = g_obs + ((size_t)e * H + h) * L::kObs;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        // output position o = t + i*J of this env's 3J-float segment comes from body o/3, component o%3
-        const int o = tt + i * J;
-        const int src = (lane_on ? a * J : 0) + o / 3, comp = o - (o / 3) * 3;
-        float x = __shfl_sync(full, lp[0], src), y = __shfl_sync(full, lp[1], src), z = __shfl_sync(full, lp[2], src);
-        float pv = comp == 0 ? x : (comp == 1 ? y : z);
-        x = __shfl_sync(full, lv[0], src); y = __shfl_sync(full, lv[1], src); z = __shfl_sync(full, lv[2], src);
-        float vv = comp == 0 ? x : (comp == 1 ? y : z);
-        if (ok) { st_stream(orow + o, pv); st_stream(orow + 3 * J + o, vv); }
+      const float a0 = hd[0], sz = hd[1], cw = hd[2];
+      const float s1 = sgn * sz, m = (c == 2) ? sz : cw;
+      const float* row = (j == 0) ? (row0_s + u * L::kRow0Floats + __float_as_int(hd[6]))
+                                  : (span_s + u * L::kSpanFloats + __float_as_int(hd[7]) + (j - 1) * kRow);
+      const float pc = row[c] - hd[3 + c], po = row[oth] - hd[3 + oth];
+      const float out_p = pc * a0 + ((s1 * po) * m) * 2.0f;
+      const float out_v = row[7 + c] * a0 + ((s1 * row[7 + oth]) * m) * 2.0f;
+      if (lane_on && e < nvalid) {
+        float* orow = g_obs + (size_t)u * L::kObs;
+        st_stream(orow + o, out_p);
+        st_stream(orow + 3 * J + o, out_v);
       }
     }
     return;
@@ -175,12 +170,20 @@ family_step_kernel(const __grid_constant__ KArgs k) {
 
   // ================= warp 0: reward / reset / tail, lane = env ==========================================
   const bool lane_env = lane < nvalid;
-  const long long env = env0 + lane;
+  const long long env = env0 + (lane_env ? lane : 0);
   long long prog = 0, reset_prev = 0;
   float pre_vx = 0.0f, pre_vz = 0.0f;
   constexpr int NF = (V == PPK_TILT) ? 3 : (V == PPK_A4) ? 6 : (V == PPK_NES) ? 2 : (V == PPK_ALIGN) ? 1 : 0;
   bool flag[NF > 0 ? NF : 1];
-  if (lane_env) {       // per-env scalars come straight from global and overlap the bulk copies
+  // per-env scalars come straight from global and overlap the bulk copies
+  const float* g_root = k.root + (size_t)env * L::kRootEnv;
+  const float* g_ball = g_root + k.ball * kRow;
+  float bx = g_ball[0], by = g_ball[1], bz = g_ball[2];
+  float bvx = g_ball[7], bvy = g_ball[8], bvz = g_ball[9];
+  float hx[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) hx[h] = g_root[k.hum[h] * kRow];
+  if (lane_env) {
     prog = k.progress[env];
     if (!(phases & PPK_PHASE_REWARD)) reset_prev = k.reset[env];
     if (phases & PPK_PHASE_REWARD) {
@@ -194,21 +197,9 @@ family_step_kernel(const __grid_constant__ KArgs k) {
   if (bulk) mbar_wait(bar, 0);
 
   const int le = (lane < TILE) ? lane : 0;     // smem row this lane reads (idle lanes read row 0)
-  const float* my_root = root_s + le * L::kRootEnv;
-  const float* ball = my_root + k.ball * kRow;
-  float bx = ball[0], by = ball[1], bz = ball[2];
-  float bvx = ball[7], bvy = ball[8], bvz = ball[9];
-  float hx[H];
-#pragma unroll
-  for (int h = 0; h < H; ++h) hx[h] = my_root[k.hum[h] * kRow];
   float dofv[2 * D];
 #pragma unroll
   for (int i = 0; i < 2 * D; ++i) dofv[i] = dof_s[le * 2 * D + i];
-  float power = 0.0f;
-  if (phases & PPK_PHASE_REWARD) {
-#pragma unroll
-    for (int d = 0; d < D; ++d) power += fabsf(force_s[le * D + d] * dofv[2 * d + 1]);
-  }
 
   long long p_new = prog + ((phases & PPK_PHASE_PROGRESS) ? 1 : 0);
   bool is_reset = reset_prev != 0;
@@ -217,6 +208,9 @@ family_step_kernel(const __grid_constant__ KArgs k) {
   for (int h = 0; h < H; ++h) rew[h] = 0.0f;
 
   if (phases & PPK_PHASE_REWARD) {
+    float power = 0.0f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) power += fabsf(force_s[le * D + d] * dofv[2 * d + 1]);
     bool die = false;
 #pragma unroll
     for (int h = 0; h < H; ++h) {
@@ -224,10 +218,15 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       s.bx = bx; s.by = by; s.bz = bz; s.vx = bvx; s.vz = bvz;
       s.pre_vx = pre_vx; s.pre_vz = pre_vz;
       const int pj = k.paddle_j[h];
+      const int u = le * H + h;
       const float* pd;
-      if (pj == 0) pd = row0_s + (le * H + h) * L::kRow0Floats + row0_off(le, h);
-      else if (pj > 0) pd = span_s + (le * H + h) * L::kSpanFloats + span_off(le, h) + (pj - 1) * kRow;
-      else pd = k.rb + ((size_t)(lane_env ? env : env0) * k.B + k.paddle_body[h]) * kRow;
+      if (pj >= 0) {
+        const int id = k.ids[h][pj > 0 ? 1 : 0];
+        const int off = bulk ? (int)((reinterpret_cast<uintptr_t>(g_rb + (size_t)le * env_stride + id * kRow) & 15u) >> 2) : 0;
+        pd = (pj == 0) ? (row0_s + u * L::kRow0Floats + off) : (span_s + u * L::kSpanFloats + off + (pj - 1) * kRow);
+      } else {
+        pd = k.rb + ((size_t)env * k.B + k.paddle_body[h]) * kRow;
+      }
       s.px = pd[0]; s.py = pd[1]; s.pz = pd[2];
       s.hx = hx[h];
       s.power_reward = (-k.power_coef) * power;
@@ -284,7 +283,11 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       const float* id = k.init_dof + (size_t)env * 2 * D;
       float* gd = k.dof + (size_t)env * 2 * D;
 #pragma unroll
-      for (int i = 0; i < 2 * D; ++i) { dofv[i] = id[i]; gd[i] = dofv[i]; }
+      for (int i = 0; i < 2 * D; ++i) {
+        const float v = id[i];
+        gd[i] = v;
+        dof_s[le * 2 * D + i] = v;      // the observation tail below reads the staged copy
+      }
     }
     p_new = 0;
   }
@@ -302,36 +305,36 @@ family_step_kernel(const __grid_constant__ KArgs k) {
   }
   if (!(phases & PPK_PHASE_OBS)) return;
 
-  // ---- ball in the heading frame; tail of the obs row goes through smem -----------------------------
-  float tail_ball[H][6];
-#pragma unroll
-  for (int h = 0; h < H; ++h) {
-    const float* r0 = row0_s + (le * H + h) * L::kRow0Floats + row0_off(le, h);
-    Heading hq = heading_quat_inv(r0[3], r0[4], r0[5], r0[6]);
-    rotate_heading(hq, bx - r0[0], by - r0[1], bz - r0[2], tail_ball[h][0], tail_ball[h][1], tail_ball[h][2]);
-    rotate_heading(hq, bvx, bvy, bvz, tail_ball[h][3], tail_ball[h][4], tail_ball[h][5]);
-  }
-  __syncwarp();   // every lane of this warp is done with root_s / dof_s / force_s (only warp 0 reads them)
+  // ---- ball in the heading frame (frames come from the obs warps) -------------------------------------
+  hdr_wait();
   if (lane < TILE) {
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      float* t = tail_s + (le * H + h) * L::kSTail;
-#pragma unroll
-      for (int d = 0; d < D; ++d) { t[d] = dofv[2 * d]; t[D + d] = dofv[2 * d + 1] * 0.1f; }
-#pragma unroll
-      for (int c = 0; c < 6; ++c) t[2 * D + c] = tail_ball[h][c];
+      const float* hd = hdr_s + (le * H + h) * L::kHdr;
+      const float a0 = hd[0], sz = hd[1], cw = hd[2];
+      const float rx = bx - hd[3], ry = by - hd[4], rz = bz - hd[5];
+      float* bs = ball_s + (le * H + h) * 6;
+      bs[0] = rx * a0 + ((-(sz * ry)) * cw) * 2.0f;
+      bs[1] = ry * a0 + ((sz * rx) * cw) * 2.0f;
+      bs[2] = rz * a0 + (sz * (sz * rz)) * 2.0f;
+      bs[3] = bvx * a0 + ((-(sz * bvy)) * cw) * 2.0f;
+      bs[4] = bvy * a0 + ((sz * bvx) * cw) * 2.0f;
+      bs[5] = bvz * a0 + (sz * (sz * bvz)) * 2.0f;
     }
   }
   __syncwarp();
-  // tail: dof_pos, 0.1*dof_vel, ball local pos/vel -- kTail contiguous floats per (env, humanoid)
-  float* g_obs = k.obs + (size_t)env0 * H * L::kObs;
-  constexpr int kTailIt = (TILE * H * L::kTail + 31) / 32;
+  // tail of the obs row, lane = element: dof_pos (D), 0.1*dof_vel (D), ball local pos/vel (6)
+  float* g_obs = k.obs + (size_t)env0 * H * L::kObs + 6 * J;
+#pragma unroll
+  for (int l = lane; l < L::kTail; l += 32) {
+    const float scale = (l >= D && l < 2 * D) ? 0.1f : 1.0f;
+    const int dsrc = (l < D) ? 2 * l : 2 * (l - D) + 1;
 #pragma unroll 4
-  for (int i = 0; i < kTailIt; ++i) {
-    int f = i * 32 + lane;
-    int eh = f / L::kTail, kk = f - eh * L::kTail;
-    int e = eh / H;
-    if (e < nvalid) st_stream(g_obs + (size_t)eh * L::kObs + 6 * J + kk, tail_s[eh * L::kSTail + kk]);
+    for (int u = 0; u < L::kUnits; ++u) {
+      const int e = u / H;
+      const float v = (l < 2 * D) ? dof_s[e * 2 * D + dsrc] * scale : ball_s[u * 6 + (l - 2 * D)];
+      if (e < nvalid) st_stream(g_obs + (size_t)u * L::kObs + l, v);
+    }
   }
 }
 
