@@ -1,23 +1,29 @@
 // Fused task step of the 27-DOF variant (humanoid_pingpong_3_actor_all_dof.py, ADOF).
 //
 // Per env the step consumes rows 0..39 of the rigid-body tensor (2080 contiguous bytes), rows
-// 0..27 of the initial (reference-pose) rigid-body tensor, 27 DOF states, their reference and the
-// DOF forces, and writes a 313-float observation row.  One warp owns a tile of 8 envs:
-//   stage    flat coalesced loads into the warp's shared-memory slice;
-//   phase B  one env per pass, lane = balance body (23) and lane = DOF (27): imitation diffs,
-//            the seven per-env reductions of compute_imitation_reward (ADOF:1313-1418) by warp
-//            shuffles, heading frames, imitation observation segments (ADOF:1891-1927);
-//   phase R  lane = env: compute_pingpong_reward_nv (ADOF:1440-1690) + compute_gradient_penalty
-//            (ADOF:1245-1301), flags, counters, time-out mask, predicated reset (ADOF:965-1028);
-//   phase P  lane = (env, body): the ten ping-pong bodies in the heading frame (ADOF:1849-1888);
-//   tail     dof / ball / reference-dof segments, lane = element.
+// 0..27 of the initial (reference-pose) rigid-body tensor, the root block, 27 DOF states, their
+// reference and the DOF forces, and writes a 313-float observation row.  One CTA of four warps owns
+// a tile of 8 envs:
+//   stage      1-D bulk async copies (cp.async.bulk / TMA engine) on one mbarrier: per env the
+//              16-byte aligned windows around its live rows (2096 B) and reference rows (1472 B),
+//              per tile the contiguous root / DOF / reference-DOF / force slices.  Tail tiles and
+//              misaligned tensors take an LDG path into the same layout.
+//   warps 1-3  one env per pass, lane = balance body (23) and lane = DOF (27): imitation diffs, the
+//              seven per-env reductions of compute_imitation_reward (ADOF:1313-1418) by warp
+//              shuffles, heading frame, imitation observation segments (ADOF:1891-1927);
+//   warp 0     the ten ping-pong bodies in the heading frame (ADOF:1849-1888, lane = output float)
+//              while the other warps reduce; then lane = env: compute_pingpong_reward_nv
+//              (ADOF:1440-1690) + compute_gradient_penalty (ADOF:1245-1301), flags, counters,
+//              time-out mask, predicated reset (ADOF:965-1028); then the dof / ball / reference-dof
+//              segments of the obs row, lane = element.
 #pragma once
+#include "ppk_async.cuh"
 #include "ppk_device.cuh"
 
 namespace ppk {
 
 constexpr int kAdofTile = 8;
-constexpr int kAdofWarps = 2;
+constexpr int kAdofThreads = 128;
 constexpr int kAdofD = 27;
 constexpr int kAdofJ = 10;       // ping-pong bodies
 constexpr int kAdofNB = 23;      // balance bodies
@@ -26,193 +32,263 @@ constexpr int kAdofInitRows = 28;  // rows 0..27 staged from the reference pose
 constexpr int kAdofObs = 6 * kAdofJ + 2 * kAdofD + 7 + 6 * kAdofNB + 2 * kAdofD;   // 313
 
 struct AdofLayout {
-  static constexpr int kRbEnv = kAdofRbRows * kRow;      // 520
+  static constexpr int kRbEnv = kAdofRbRows * kRow;      // 520 floats used
   static constexpr int kInitEnv = kAdofInitRows * kRow;  // 364
-  static constexpr int kSRb = kRbEnv | 1;
-  static constexpr int kSInit = kInitEnv | 1;
-  static constexpr int kSRoot = 3 * kRow;                // 39
-  static constexpr int kSDof = (2 * kAdofD) | 1;         // 55
-  static constexpr int kSForce = kAdofD;                 // 27
+  static constexpr int kSRb = ((kRbEnv + 3 + 3) / 4) * 4;      // 524: window incl. alignment slack
+  static constexpr int kSInit = ((kInitEnv + 3 + 3) / 4) * 4;  // 368
+  static constexpr int kRoot = 3 * kRow;                 // 39, dense
+  static constexpr int kDof = 2 * kAdofD;                // 54, dense
   static constexpr int kSHdr = 24;
   static constexpr int kOffInit = kAdofTile * kSRb;
   static constexpr int kOffRoot = kOffInit + kAdofTile * kSInit;
-  static constexpr int kOffDof = kOffRoot + kAdofTile * kSRoot;
-  static constexpr int kOffIDof = kOffDof + kAdofTile * kSDof;
-  static constexpr int kOffForce = kOffIDof + kAdofTile * kSDof;
-  static constexpr int kOffHdr = kOffForce + kAdofTile * kSForce;
-  static constexpr int kWarpFloats = kOffHdr + kAdofTile * kSHdr;
+  static constexpr int kOffDof = kOffRoot + kAdofTile * kRoot;
+  static constexpr int kOffIDof = kOffDof + kAdofTile * kDof;
+  static constexpr int kOffForce = kOffIDof + kAdofTile * kDof;
+  static constexpr int kOffHdr = kOffForce + kAdofTile * kAdofD;
+  static constexpr int kOffBar = kOffHdr + kAdofTile * kSHdr;
+  static constexpr int kFloats = kOffBar + 4;
+  static constexpr uint32_t kTxBytes =
+      4u * (kAdofTile * (kSRb + kSInit) + kAdofTile * kRoot + 2 * kAdofTile * kDof + kAdofTile * kAdofD);
+  static_assert((kAdofTile * kRoot) % 4 == 0 && (kAdofTile * kDof) % 4 == 0 && (kAdofTile * kAdofD) % 4 == 0, "bulk sizes");
+  static_assert(kOffInit % 4 == 0 && kOffRoot % 4 == 0 && kOffDof % 4 == 0 && kOffIDof % 4 == 0 && kOffForce % 4 == 0,
+                "bulk destinations are 16-byte aligned");
+  static_assert(kOffBar % 2 == 0, "mbarrier alignment");
 };
 // hdr slots per env
-enum { H_RX = 0, H_RY, H_RZ, H_SZ, H_CW,            // ping-pong heading frame (body ids[0])
-       H_SUM_DP2, H_SUM_DV2, H_SUM_NORM,            // balance-body reductions
-       H_SUM_DQ22, H_SUM_DQ5, H_SUM_DQD22, H_POWER, // DOF reductions
+enum { H_A0 = 0, H_SZ, H_CW, H_RX, H_RY, H_RZ,        // ping-pong heading frame (body ids[0])
+       H_SUM_DP2, H_SUM_DV2, H_SUM_NORM,              // balance-body reductions
+       H_SUM_DQ22, H_SUM_DQ5, H_SUM_DQD22, H_POWER,   // DOF reductions
        H_BALL0, H_BALL1, H_BALL2, H_BALL3, H_BALL4, H_BALL5, H_BALL6 };
 
-template <int ITERS, int ENV_FLOATS, int S>
-__device__ __forceinline__ void stage_flat(float* dst, const float* g, int valid_floats, int lane) {
-  // the tile's slice is contiguous in global memory: float f of the slice -> dst[(f / ENV)*S + f % ENV]
-  constexpr int kBatch = ITERS > 48 ? 48 : ITERS;
-#pragma unroll 1
-  for (int it0 = 0; it0 < ITERS; it0 += kBatch) {
-    float v[kBatch];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      int f = (it0 + u) * 32 + lane;
-      v[u] = (it0 + u < ITERS && f < valid_floats) ? ld_stream(g + f) : 0.0f;
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      int f = (it0 + u) * 32 + lane;
-      int e = f / ENV_FLOATS, r = f - e * ENV_FLOATS;
-      if (it0 + u < ITERS && e < kAdofTile) dst[e * S + r] = v[u];
-    }
-  }
-}
+// named barrier 2: warps 1-3 arrive when the per-env reductions / frames are in hdr_s, warp 0 waits
+__device__ __forceinline__ void adof_arrive() { asm volatile("bar.arrive 2, %0;" ::"n"(kAdofThreads) : "memory"); }
+__device__ __forceinline__ void adof_wait() { asm volatile("bar.sync 2, %0;" ::"n"(kAdofThreads) : "memory"); }
 
-template <int ITERS, int ENV_FLOATS, int S>
-__device__ __forceinline__ void stage_rows(float* dst, const float* g, int env_stride, int nvalid, int lane) {
-  // ENV_FLOATS contiguous floats per env, envs env_stride floats apart
-  constexpr int kBatch = ITERS > 48 ? 48 : ITERS;
-#pragma unroll 1
-  for (int it0 = 0; it0 < ITERS; it0 += kBatch) {
-    float v[kBatch];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      int f = (it0 + u) * 32 + lane;
-      int e = f / ENV_FLOATS, r = f - e * ENV_FLOATS;
-      v[u] = (it0 + u < ITERS && e < nvalid) ? ld_stream(g + (size_t)e * env_stride + r) : 0.0f;
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      int f = (it0 + u) * 32 + lane;
-      int e = f / ENV_FLOATS, r = f - e * ENV_FLOATS;
-      if (it0 + u < ITERS && e < kAdofTile) dst[e * S + r] = v[u];
-    }
-  }
-}
+constexpr uint32_t kPhaseDeferCounterClear = 1u << 8;   // internal (host session): clear counters once per shard
 
-__global__ void __launch_bounds__(kAdofWarps * 32)
+__global__ void __launch_bounds__(kAdofThreads, 6)
 adof_step_kernel(const __grid_constant__ KArgs k) {
   using L = AdofLayout;
-  extern __shared__ float smem[];
+  extern __shared__ __align__(128) float smem[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long tile = (long long)blockIdx.x * kAdofWarps + warp;
-  const long long env0 = tile * kAdofTile;
-  if (env0 >= k.n) return;
+  const long long env0 = (long long)blockIdx.x * kAdofTile;
   const int nvalid = (int)min((long long)kAdofTile, k.n - env0);
   constexpr int D = kAdofD, J = kAdofJ, NB = kAdofNB, T = kAdofTile;
 
-  float* rb_s = smem + (size_t)warp * L::kWarpFloats;
-  float* init_s = rb_s + L::kOffInit;
-  float* root_s = rb_s + L::kOffRoot;
-  float* dof_s = rb_s + L::kOffDof;
-  float* idof_s = rb_s + L::kOffIDof;
-  float* force_s = rb_s + L::kOffForce;
-  float* hdr_s = rb_s + L::kOffHdr;
+  float* rb_s = smem;
+  float* init_s = smem + L::kOffInit;
+  float* root_s = smem + L::kOffRoot;
+  float* dof_s = smem + L::kOffDof;
+  float* idof_s = smem + L::kOffIDof;
+  float* force_s = smem + L::kOffForce;
+  float* hdr_s = smem + L::kOffHdr;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   const int phases = k.phases;
+  const bool bulk = k.bulk_ok && (nvalid == T);
+  const int env_stride = k.B * kRow;
+  const float* g_rb = k.rb + (size_t)env0 * env_stride;
+  const float* g_init = k.init_rb + (size_t)env0 * env_stride;
+
+  // position of env e's row 0 inside its 16-byte aligned staging window (floats)
+  auto win_off = [&](const float* base, int e) -> int {
+    return bulk ? (int)((reinterpret_cast<uintptr_t>(base + (size_t)e * env_stride) & 15u) >> 2) : 0;
+  };
 
   // ---- stage -------------------------------------------------------------------------------
-  stage_flat<(T * 39 + 31) / 32, 39, L::kSRoot>(root_s, k.root + (size_t)env0 * 39, nvalid * 39, lane);
-  stage_flat<(T * 2 * D + 31) / 32, 2 * D, L::kSDof>(dof_s, k.dof + (size_t)env0 * 2 * D, nvalid * 2 * D, lane);
-  stage_flat<(T * 2 * D + 31) / 32, 2 * D, L::kSDof>(idof_s, k.init_dof + (size_t)env0 * 2 * D, nvalid * 2 * D, lane);
-  stage_flat<(T * D + 31) / 32, D, L::kSForce>(force_s, k.force + (size_t)env0 * D, nvalid * D, lane);
-  stage_rows<(T * L::kRbEnv + 31) / 32, L::kRbEnv, L::kSRb>(rb_s, k.rb + (size_t)env0 * k.B * kRow, k.B * kRow, nvalid, lane);
-  stage_rows<(T * L::kInitEnv + 31) / 32, L::kInitEnv, L::kSInit>(init_s, k.init_rb + (size_t)env0 * k.B * kRow, k.B * kRow, nvalid, lane);
-  __syncwarp();
-
-  float* g_obs = k.obs + (size_t)env0 * kAdofObs;
-  const int bal_id = (lane < NB) ? k.bal_ids[lane] : k.bal_ids[0];
-  const int bal_root = k.bal_ids[0];
-  const int pp_root = k.ids[0][0];
-
-  // ---- phase B: one env per pass; lane = balance body and lane = DOF -----------------------------
-#pragma unroll 1
-  for (int e = 0; e < T; ++e) {
-    const float* rb_e = rb_s + e * L::kSRb;
-    const float* in_e = init_s + e * L::kSInit;
-    const float* cur = rb_e + bal_id * kRow;
-    const float* ref = in_e + bal_id * kRow;
-    const bool body_on = lane < NB;
-    // imitation diffs: ref - cur (ADOF:1345,1349 / ADOF:1908-1909)
-    float dpx = ref[0] - cur[0], dpy = ref[1] - cur[1], dpz = ref[2] - cur[2];
-    float dvx = ref[7] - cur[7], dvy = ref[8] - cur[8], dvz = ref[9] - cur[9];
-    // has_fallen uses cur - ref (ADOF:1412)
-    float nx = cur[0] - ref[0], ny = cur[1] - ref[1], nz = cur[2] - ref[2];
-    float s_dp2 = body_on ? (dpx * dpx + dpy * dpy + dpz * dpz) / 3.0f : 0.0f;
-    float s_dv2 = body_on ? (dvx * dvx + dvy * dvy + dvz * dvz) / 3.0f : 0.0f;
-    float s_nrm = body_on ? sqrtf(nx * nx + ny * ny + nz * nz) : 0.0f;
-    // DOF terms, lane = DOF index
-    const bool dof_on = lane < D;
-    const int dl = dof_on ? lane : 0;
-    float q = dof_s[e * L::kSDof + 2 * dl], qd = dof_s[e * L::kSDof + 2 * dl + 1];
-    float rq = idof_s[e * L::kSDof + 2 * dl], rqd = idof_s[e * L::kSDof + 2 * dl + 1];
-    float dq = rq - q, dqd = rqd - qd;
-    float s_dq22 = (dof_on && lane < 22) ? dq * dq : 0.0f;
-    float s_dq5 = (dof_on && lane >= 22) ? dq * dq : 0.0f;
-    float s_dqd22 = (dof_on && lane < 22) ? dqd * dqd : 0.0f;
-    float s_pow = dof_on ? fabsf(force_s[e * L::kSForce + dl] * qd) : 0.0f;
-    s_dp2 = warp_sum(s_dp2); s_dv2 = warp_sum(s_dv2); s_nrm = warp_sum(s_nrm);
-    s_dq22 = warp_sum(s_dq22); s_dq5 = warp_sum(s_dq5); s_dqd22 = warp_sum(s_dqd22); s_pow = warp_sum(s_pow);
-    // heading frames: ping-pong root body and balance root body (both row 0 in the shipped config)
-    const float* r0 = rb_e + pp_root * kRow;
-    Heading hq_pp = heading_quat_inv(r0[3], r0[4], r0[5], r0[6]);
-    const float* b0 = rb_e + bal_root * kRow;
-    Heading hq_bal = (bal_root == pp_root) ? hq_pp : heading_quat_inv(b0[3], b0[4], b0[5], b0[6]);
-    if (lane == 0) {
-      float* hd = hdr_s + e * L::kSHdr;
-      hd[H_RX] = r0[0]; hd[H_RY] = r0[1]; hd[H_RZ] = r0[2]; hd[H_SZ] = hq_pp.sz; hd[H_CW] = hq_pp.cw;
-      hd[H_SUM_DP2] = s_dp2; hd[H_SUM_DV2] = s_dv2; hd[H_SUM_NORM] = s_nrm;
-      hd[H_SUM_DQ22] = s_dq22; hd[H_SUM_DQ5] = s_dq5; hd[H_SUM_DQD22] = s_dqd22; hd[H_POWER] = s_pow;
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      mbar_fence_init();
     }
-    if ((phases & PPK_PHASE_OBS) && e < nvalid) {
-      // imitation observation segments [121,190) = 10*R(dP), [190,259) = R(dV)
-      float lp[3], lv[3];
-      rotate_heading(hq_bal, dpx, dpy, dpz, lp[0], lp[1], lp[2]);
-      rotate_heading(hq_bal, dvx, dvy, dvz, lv[0], lv[1], lv[2]);
-      lp[0] *= 10.0f; lp[1] *= 10.0f; lp[2] *= 10.0f;
-      float* orow = g_obs + (size_t)e * kAdofObs + (6 * J + 2 * D + 7);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int o = (body_on ? lane : 0) + i * NB;
-        const int src = o / 3, comp = o - src * 3;
-        float x = __shfl_sync(full, lp[0], src), y = __shfl_sync(full, lp[1], src), z = __shfl_sync(full, lp[2], src);
-        float pv = comp == 0 ? x : (comp == 1 ? y : z);
-        x = __shfl_sync(full, lv[0], src); y = __shfl_sync(full, lv[1], src); z = __shfl_sync(full, lv[2], src);
-        float vv = comp == 0 ? x : (comp == 1 ? y : z);
-        if (body_on) { st_stream(orow + o, pv); st_stream(orow + 3 * NB + o, vv); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(bar, L::kTxBytes);
+      bulk_g2s(root_s, k.root + (size_t)env0 * L::kRoot, 4u * T * L::kRoot, bar);
+      bulk_g2s(dof_s, k.dof + (size_t)env0 * L::kDof, 4u * T * L::kDof, bar);
+      bulk_g2s(idof_s, k.init_dof + (size_t)env0 * L::kDof, 4u * T * L::kDof, bar);
+      bulk_g2s(force_s, k.force + (size_t)env0 * D, 4u * T * D, bar);
+    }
+    if (lane < 4) {       // 16 windows, four per warp
+      const int i = warp * 4 + lane;
+      const int e = i >> 1;
+      if (i & 1) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(g_init + (size_t)e * env_stride) & ~(uintptr_t)15;
+        bulk_g2s(init_s + e * L::kSInit, reinterpret_cast<const void*>(a), 4u * L::kSInit, bar);
+      } else {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(g_rb + (size_t)e * env_stride) & ~(uintptr_t)15;
+        bulk_g2s(rb_s + e * L::kSRb, reinterpret_cast<const void*>(a), 4u * L::kSRb, bar);
       }
     }
+  } else {
+    for (int f = threadIdx.x; f < T * L::kRbEnv; f += kAdofThreads) {
+      const int e = f / L::kRbEnv, r = f - e * L::kRbEnv;
+      rb_s[e * L::kSRb + r] = (e < nvalid) ? g_rb[(size_t)e * env_stride + r] : 0.0f;
+    }
+    for (int f = threadIdx.x; f < T * L::kInitEnv; f += kAdofThreads) {
+      const int e = f / L::kInitEnv, r = f - e * L::kInitEnv;
+      init_s[e * L::kSInit + r] = (e < nvalid) ? g_init[(size_t)e * env_stride + r] : 0.0f;
+    }
+    for (int f = threadIdx.x; f < T * L::kRoot; f += kAdofThreads)
+      root_s[f] = (f < nvalid * L::kRoot) ? k.root[(size_t)env0 * L::kRoot + f] : 0.0f;
+    for (int f = threadIdx.x; f < T * L::kDof; f += kAdofThreads) {
+      dof_s[f] = (f < nvalid * L::kDof) ? k.dof[(size_t)env0 * L::kDof + f] : 0.0f;
+      idof_s[f] = (f < nvalid * L::kDof) ? k.init_dof[(size_t)env0 * L::kDof + f] : 0.0f;
+    }
+    for (int f = threadIdx.x; f < T * D; f += kAdofThreads)
+      force_s[f] = (f < nvalid * D) ? k.force[(size_t)env0 * D + f] : 0.0f;
+    __syncthreads();
   }
-  __syncwarp();
 
-  // ---- phase R: lane = env ---------------------------------------------------------------------
+  float* g_obs = k.obs + (size_t)env0 * kAdofObs;
+  const int pp_root = k.ids[0][0];
+
+  if (warp != 0) {
+    // ================= warps 1-3: one env per pass; lane = balance body and lane = DOF ==============
+    if (bulk) mbar_wait(bar, 0);
+    const int bal_id = (lane < NB) ? k.bal_ids[lane] : k.bal_ids[0];
+    const int bal_root = k.bal_ids[0];
+    // heading frames of this warp's envs, computed once with lane = pass slot and broadcast per pass
+    Heading my_hq; my_hq.sz = 0.0f; my_hq.cw = 1.0f;
+    {
+      const int e = (warp - 1) + 3 * lane;
+      if (e < T) {
+        const float* r0 = rb_s + e * L::kSRb + win_off(g_rb, e) + pp_root * kRow;
+        my_hq = heading_quat_inv(r0[3], r0[4], r0[5], r0[6]);
+      }
+    }
+    int slot = 0;
+#pragma unroll 1
+    for (int e = warp - 1; e < T; e += 3, ++slot) {
+      const float* rb_e = rb_s + e * L::kSRb + win_off(g_rb, e);
+      const float* in_e = init_s + e * L::kSInit + win_off(g_init, e);
+      const float* cur = rb_e + bal_id * kRow;
+      const float* ref = in_e + bal_id * kRow;
+      const bool body_on = lane < NB;
+      // imitation diffs: ref - cur (ADOF:1345,1349 / ADOF:1908-1909)
+      float dpx = ref[0] - cur[0], dpy = ref[1] - cur[1], dpz = ref[2] - cur[2];
+      float dvx = ref[7] - cur[7], dvy = ref[8] - cur[8], dvz = ref[9] - cur[9];
+      // has_fallen uses cur - ref (ADOF:1412)
+      float nx = cur[0] - ref[0], ny = cur[1] - ref[1], nz = cur[2] - ref[2];
+      float s_dp2 = body_on ? (dpx * dpx + dpy * dpy + dpz * dpz) / 3.0f : 0.0f;
+      float s_dv2 = body_on ? (dvx * dvx + dvy * dvy + dvz * dvz) / 3.0f : 0.0f;
+      float s_nrm = body_on ? sqrtf(nx * nx + ny * ny + nz * nz) : 0.0f;
+      // DOF terms, lane = DOF index
+      const bool dof_on = lane < D;
+      const int dl = dof_on ? lane : 0;
+      float q = dof_s[e * L::kDof + 2 * dl], qd = dof_s[e * L::kDof + 2 * dl + 1];
+      float rq = idof_s[e * L::kDof + 2 * dl], rqd = idof_s[e * L::kDof + 2 * dl + 1];
+      float dq = rq - q, dqd = rqd - qd;
+      float s_dq22 = (dof_on && lane < 22) ? dq * dq : 0.0f;
+      float s_dq5 = (dof_on && lane >= 22) ? dq * dq : 0.0f;
+      float s_dqd22 = (dof_on && lane < 22) ? dqd * dqd : 0.0f;
+      float s_pow = dof_on ? fabsf(force_s[e * D + dl] * qd) : 0.0f;
+      s_dp2 = warp_sum(s_dp2); s_dv2 = warp_sum(s_dv2); s_nrm = warp_sum(s_nrm);
+      s_dq22 = warp_sum(s_dq22); s_dq5 = warp_sum(s_dq5); s_dqd22 = warp_sum(s_dqd22); s_pow = warp_sum(s_pow);
+      // heading frames: ping-pong root body and balance root body (both row 0 in the shipped config)
+      const float* r0 = rb_e + pp_root * kRow;
+      Heading hq_pp;
+      hq_pp.sz = __shfl_sync(full, my_hq.sz, slot);
+      hq_pp.cw = __shfl_sync(full, my_hq.cw, slot);
+      const float* b0 = rb_e + bal_root * kRow;
+      Heading hq_bal = (bal_root == pp_root) ? hq_pp : heading_quat_inv(b0[3], b0[4], b0[5], b0[6]);
+      if (lane == 0) {
+        float* hd = hdr_s + e * L::kSHdr;
+        hd[H_A0] = 2.0f * (hq_pp.cw * hq_pp.cw) - 1.0f; hd[H_SZ] = hq_pp.sz; hd[H_CW] = hq_pp.cw;
+        hd[H_RX] = r0[0]; hd[H_RY] = r0[1]; hd[H_RZ] = r0[2];
+        hd[H_SUM_DP2] = s_dp2; hd[H_SUM_DV2] = s_dv2; hd[H_SUM_NORM] = s_nrm;
+        hd[H_SUM_DQ22] = s_dq22; hd[H_SUM_DQ5] = s_dq5; hd[H_SUM_DQD22] = s_dqd22; hd[H_POWER] = s_pow;
+      }
+      if ((phases & PPK_PHASE_OBS) && e < nvalid) {
+        // imitation observation segments [121,190) = 10*R(dP), [190,259) = R(dV)
+        float lp[3], lv[3];
+        rotate_heading(hq_bal, dpx, dpy, dpz, lp[0], lp[1], lp[2]);
+        rotate_heading(hq_bal, dvx, dvy, dvz, lv[0], lv[1], lv[2]);
+        lp[0] *= 10.0f; lp[1] *= 10.0f; lp[2] *= 10.0f;
+        float* orow = g_obs + (size_t)e * kAdofObs + (6 * J + 2 * D + 7);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int o = (body_on ? lane : 0) + i * NB;
+          const int src = o / 3, comp = o - src * 3;
+          float x = __shfl_sync(full, lp[0], src), y = __shfl_sync(full, lp[1], src), z = __shfl_sync(full, lp[2], src);
+          float pv = comp == 0 ? x : (comp == 1 ? y : z);
+          x = __shfl_sync(full, lv[0], src); y = __shfl_sync(full, lv[1], src); z = __shfl_sync(full, lv[2], src);
+          float vv = comp == 0 ? x : (comp == 1 ? y : z);
+          if (body_on) { st_stream(orow + o, pv); st_stream(orow + 3 * NB + o, vv); }
+        }
+      }
+    }
+    adof_arrive();
+    return;
+  }
+
+  // ================= warp 0 =================================================================
+  // per-env scalars straight from global, overlapping the bulk copies (lane = env)
   const bool lane_env = lane < nvalid;
   const int le = (lane < T) ? lane : 0;
-  const long long env = env0 + le;
-  float* hd = hdr_s + le * L::kSHdr;
-  const float* my_root = root_s + le * L::kSRoot;
-  const float* ball = my_root + k.ball * kRow;
-  float bx = ball[0], by = ball[1], bz = ball[2], bvx = ball[7], bvy = ball[8], bvz = ball[9];
+  const long long env = env0 + (lane_env ? lane : 0);
   long long prog = 0, reset_prev = 0;
+  float pre_vx = 0.0f;
+  bool f_pcc = false, f_htc = false, f_dpc = false, f_hdc = false;
+  bool c_closer = false, c_hitp = false, c_net = false, c_table = false, c_fall = false;
   if (lane_env) {
     prog = k.progress[env];
     if (!(phases & PPK_PHASE_REWARD)) reset_prev = k.reset[env];
-  }
-  long long p_new = prog + ((phases & PPK_PHASE_PROGRESS) ? 1 : 0);
-  bool is_reset = reset_prev != 0;
-  float reward = 0.0f;
-  bool f_pcc = false, f_htc = false, f_dpc = false, f_hdc = false;
-  bool c_closer = false, c_hitp = false, c_net = false, c_table = false, c_fall = false;
-
-  if (phases & PPK_PHASE_REWARD) {
-    float pre_vx = 0.0f;
-    if (lane_env) {
+    if (phases & PPK_PHASE_REWARD) {
       pre_vx = ld_stream(k.pre + (size_t)env * k.pre_stride + k.pre_vx);
       f_pcc = k.flags[0][env] != 0; f_htc = k.flags[1][env] != 0; f_dpc = k.flags[2][env] != 0; f_hdc = k.flags[3][env] != 0;
       c_closer = k.flags[4][env] != 0; c_hitp = k.flags[5][env] != 0; c_net = k.flags[6][env] != 0;
       c_table = k.flags[7][env] != 0; c_fall = k.flags[8][env] != 0;
     }
+  }
+  if (bulk) mbar_wait(bar, 0);
+
+  // ---- ping-pong bodies, lane = output float (needs only the heading frame of its env) ------------
+  if (phases & PPK_PHASE_OBS) {
+    const bool lane_on = lane < 3 * J;
+    const int o = lane_on ? lane : 0;
+    const int j = o / 3, c = o - j * 3;
+    const int oth = (c == 0) ? 1 : (c == 1 ? 0 : 2);
+    const float sgn = (c == 0) ? -1.0f : 1.0f;
+    const int my_id = k.ids[0][j];
+    // frames recomputed here (lane = env, then broadcast) instead of waiting for the reducing warps
+    Heading my_hq; my_hq.sz = 0.0f; my_hq.cw = 1.0f;
+    if (lane < T) {
+      const float* r0 = rb_s + lane * L::kSRb + win_off(g_rb, lane) + pp_root * kRow;
+      my_hq = heading_quat_inv(r0[3], r0[4], r0[5], r0[6]);
+    }
+#pragma unroll 2
+    for (int e = 0; e < T; ++e) {
+      const float* rb_e = rb_s + e * L::kSRb + win_off(g_rb, e);
+      const float* r0 = rb_e + pp_root * kRow;
+      Heading hq;
+      hq.sz = __shfl_sync(full, my_hq.sz, e);
+      hq.cw = __shfl_sync(full, my_hq.cw, e);
+      const float a0 = 2.0f * (hq.cw * hq.cw) - 1.0f;
+      const float s1 = sgn * hq.sz, m = (c == 2) ? hq.sz : hq.cw;
+      const float* row = rb_e + my_id * kRow;
+      const float pc = row[c] - r0[c], po = row[oth] - r0[oth];
+      const float out_p = pc * a0 + ((s1 * po) * m) * 2.0f;
+      const float out_v = row[7 + c] * a0 + ((s1 * row[7 + oth]) * m) * 2.0f;
+      if (lane_on && e < nvalid) {
+        float* orow = g_obs + (size_t)e * kAdofObs;
+        st_stream(orow + o, out_p);
+        st_stream(orow + 3 * J + o, out_v);
+      }
+    }
+  }
+
+  // ---- phase R: lane = env ---------------------------------------------------------------------
+  adof_wait();          // reductions and frames of all 8 envs are in hdr_s
+  float* hd = hdr_s + le * L::kSHdr;
+  const float* my_root = root_s + le * L::kRoot;
+  const float* ball = my_root + k.ball * kRow;
+  float bx = ball[0], by = ball[1], bz = ball[2], bvx = ball[7], bvy = ball[8], bvz = ball[9];
+  long long p_new = prog + ((phases & PPK_PHASE_PROGRESS) ? 1 : 0);
+  bool is_reset = reset_prev != 0;
+  float reward = 0.0f;
+
+  if (phases & PPK_PHASE_REWARD) {
     // compute_imitation_reward, is_g1 branch (ADOF:1330-1418)
     float r_body_pos = expf(-50.0f * (hd[H_SUM_DP2] / (float)NB));
     float r_body_vel = expf(-4.0f * (hd[H_SUM_DV2] / (float)NB));
@@ -224,9 +300,10 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
     if (has_fallen) ref_reward = 1.0f * -50.0f;
     c_fall = c_fall || has_fallen;
 
-    const float* pd = rb_s + le * L::kSRb + k.paddle_body[0] * kRow;
+    const float* rb_e = rb_s + le * L::kSRb + win_off(g_rb, le);
+    const float* pd = rb_e + k.paddle_body[0] * kRow;
     float px = pd[0], py = pd[1], pz = pd[2];
-    float pelvis_z = rb_s[le * L::kSRb + k.pelvis_body * kRow + 2];
+    float pelvis_z = rb_e[k.pelvis_body * kRow + 2];
     float hx = my_root[k.hum[0] * kRow];
     bool x_close = fabsf(bx - px) < 0.2f;
     bool first_close = x_close && !f_pcc;
@@ -280,7 +357,7 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
 #pragma unroll
     for (int i = 0; i < PPK_NUM_STATS; ++i) v[i] = warp_sum(v[i]);
     if (lane == 0) {
-      double* slot = k.stats + (size_t)(tile % PPK_STATS_SLOTS) * PPK_NUM_STATS;
+      double* slot = k.stats + (size_t)(blockIdx.x % PPK_STATS_SLOTS) * PPK_NUM_STATS;
 #pragma unroll
       for (int i = 0; i < PPK_NUM_STATS; ++i) atomicAdd(slot + i, v[i]);
     }
@@ -306,8 +383,8 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
     if (k.reset_dof) {
       float* gd = k.dof + (size_t)env * 2 * D;
       for (int i = 0; i < 2 * D; ++i) {
-        float v = idof_s[le * L::kSDof + i];
-        dof_s[le * L::kSDof + i] = v;
+        float v = idof_s[le * L::kDof + i];
+        dof_s[le * L::kDof + i] = v;
         gd[i] = v;
       }
     }
@@ -327,70 +404,39 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
 
   // ball in the heading frame (+ y-intersect, ADOF:1833-1839)
   if (lane < T) {
-    Heading hq; hq.sz = hd[H_SZ]; hq.cw = hd[H_CW];
-    float lp[3], lv[3];
-    rotate_heading(hq, bx - hd[H_RX], by - hd[H_RY], bz - hd[H_RZ], lp[0], lp[1], lp[2]);
-    rotate_heading(hq, bvx, bvy, bvz, lv[0], lv[1], lv[2]);
-    float yi = lp[1] + (lv[1] / (-lv[0] + 1e-6f)) * lp[0];
-    hd[H_BALL0] = lp[0]; hd[H_BALL1] = lp[1]; hd[H_BALL2] = lp[2];
-    hd[H_BALL3] = lv[0]; hd[H_BALL4] = lv[1]; hd[H_BALL5] = lv[2]; hd[H_BALL6] = yi;
+    const float a0 = hd[H_A0], sz = hd[H_SZ], cw = hd[H_CW];
+    const float rx = bx - hd[H_RX], ry = by - hd[H_RY], rz = bz - hd[H_RZ];
+    const float lp0 = rx * a0 + ((-(sz * ry)) * cw) * 2.0f;
+    const float lp1 = ry * a0 + ((sz * rx) * cw) * 2.0f;
+    const float lp2 = rz * a0 + (sz * (sz * rz)) * 2.0f;
+    const float lv0 = bvx * a0 + ((-(sz * bvy)) * cw) * 2.0f;
+    const float lv1 = bvy * a0 + ((sz * bvx) * cw) * 2.0f;
+    const float lv2 = bvz * a0 + (sz * (sz * bvz)) * 2.0f;
+    const float yi = lp1 + (lv1 / (-lv0 + 1e-6f)) * lp0;
+    hd[H_BALL0] = lp0; hd[H_BALL1] = lp1; hd[H_BALL2] = lp2;
+    hd[H_BALL3] = lv0; hd[H_BALL4] = lv1; hd[H_BALL5] = lv2; hd[H_BALL6] = yi;
   }
   __syncwarp();
-
-  // ---- phase P: lane = (env a of the pass, ping-pong body t) ------------------------------------
-  {
-    constexpr int P = 32 / J;
-    const int a = lane / J, t = lane - a * J;
-    const int my_id = k.ids[0][(a < P) ? t : 0];
-#pragma unroll 1
-    for (int pass = 0; pass * P < T; ++pass) {
-      const int e = pass * P + a;
-      const bool ok = (a < P) && (e < nvalid);
-      const int ec = (ok ? e : 0);
-      const float* hh = hdr_s + ec * L::kSHdr;
-      Heading hq; hq.sz = hh[H_SZ]; hq.cw = hh[H_CW];
-      const float* row = rb_s + ec * L::kSRb + my_id * kRow;
-      float lp[3], lv[3];
-      rotate_heading(hq, row[0] - hh[H_RX], row[1] - hh[H_RY], row[2] - hh[H_RZ], lp[0], lp[1], lp[2]);
-      rotate_heading(hq, row[7], row[8], row[9], lv[0], lv[1], lv[2]);
-      float* orow = g_obs + (size_t)e * kAdofObs;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int o = t + i * J;
-        const int src = (a < P ? a * J : 0) + o / 3, comp = o - (o / 3) * 3;
-        float x = __shfl_sync(full, lp[0], src), y = __shfl_sync(full, lp[1], src), z = __shfl_sync(full, lp[2], src);
-        float pv = comp == 0 ? x : (comp == 1 ? y : z);
-        x = __shfl_sync(full, lv[0], src); y = __shfl_sync(full, lv[1], src); z = __shfl_sync(full, lv[2], src);
-        float vv = comp == 0 ? x : (comp == 1 ? y : z);
-        if (ok) { st_stream(orow + o, pv); st_stream(orow + 3 * J + o, vv); }
-      }
-    }
-  }
   // ---- tail segments, lane = element ------------------------------------------------------------
   // [60,121): dof_pos, 0.1*dof_vel, ball local pos/vel, y_intersect; [259,313): reference dof pos/vel
   constexpr int kSegA = 2 * D + 7, kSegB = 2 * D;
-#pragma unroll 1
-  for (int f = lane; f < T * (kSegA + kSegB); f += 32) {
-    int e = f / (kSegA + kSegB), kk = f - e * (kSegA + kSegB);
-    if (e >= nvalid) continue;
-    float v;
-    int o;
-    if (kk < kSegA) {
-      o = 6 * J + kk;
-      if (kk < D) v = dof_s[e * L::kSDof + 2 * kk];
-      else if (kk < 2 * D) v = dof_s[e * L::kSDof + 2 * (kk - D) + 1] * 0.1f;
-      else v = hdr_s[e * L::kSHdr + H_BALL0 + (kk - 2 * D)];
-    } else {
-      int r = kk - kSegA;
-      o = 6 * J + kSegA + 6 * NB + r;
-      v = (r < D) ? idof_s[e * L::kSDof + 2 * r] : idof_s[e * L::kSDof + 2 * (r - D) + 1];
-    }
-    st_stream(g_obs + (size_t)e * kAdofObs + o, v);
+#pragma unroll
+  for (int l = lane; l < kSegA + kSegB; l += 32) {
+    // per-lane source: which staged array, which element, which scale
+    const float* src;
+    int stride, oo;
+    float scale = 1.0f;
+    if (l < D) { src = dof_s + 2 * l; stride = L::kDof; }
+    else if (l < 2 * D) { src = dof_s + 2 * (l - D) + 1; stride = L::kDof; scale = 0.1f; }
+    else if (l < kSegA) { src = hdr_s + H_BALL0 + (l - 2 * D); stride = L::kSHdr; }
+    else if (l < kSegA + D) { src = idof_s + 2 * (l - kSegA); stride = L::kDof; }
+    else { src = idof_s + 2 * (l - kSegA - D) + 1; stride = L::kDof; }
+    oo = (l < kSegA) ? (6 * J + l) : (6 * J + kSegA + 6 * NB + (l - kSegA));
+#pragma unroll
+    for (int e = 0; e < T; ++e)
+      if (e < nvalid) st_stream(g_obs + (size_t)e * kAdofObs + oo, src[e * stride] * scale);
   }
 }
-
-// internal phase bit (host session): the counter clear is issued once per shard, not per chunk
-constexpr uint32_t kPhaseDeferCounterClear = 1u << 8;
 
 inline int launch_adof_clear(unsigned int* scratch, unsigned char* const* flags, long long n, cudaStream_t s) {
   long long cb = (n / 4 + 255) / 256;
@@ -400,15 +446,20 @@ inline int launch_adof_clear(unsigned int* scratch, unsigned char* const* flags,
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 
-inline int launch_adof(const KArgs& k, cudaStream_t s) {
-  // staged row windows: live rows 0..39, reference rows 0..27
+inline int launch_adof(const KArgs& k0, cudaStream_t s) {
+  KArgs k = k0;
+  // staged row windows: live rows 0..39, reference rows 0..27 (+ one following row for the window slack)
   if (k.B < kAdofRbRows) return PPK_ERR_SHAPE;
   for (int j = 0; j < kAdofJ; ++j)
     if (k.ids[0][j] >= kAdofRbRows) return PPK_ERR_SHAPE;
   for (int j = 0; j < kAdofNB; ++j)
     if (k.bal_ids[j] >= kAdofInitRows) return PPK_ERR_SHAPE;
   if (k.paddle_body[0] >= kAdofRbRows || k.pelvis_body >= kAdofRbRows) return PPK_ERR_SHAPE;
-  constexpr size_t smem = (size_t)kAdofWarps * AdofLayout::kWarpFloats * sizeof(float);
+  const void* al[] = {k.rb, k.init_rb, k.root, k.dof, k.init_dof, k.force};
+  bool bulk = k.B > kAdofRbRows;
+  for (const void* p : al) bulk = bulk && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
+  k.bulk_ok = bulk ? 1 : 0;
+  constexpr size_t smem = (size_t)AdofLayout::kFloats * sizeof(float);
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(adof_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -424,8 +475,7 @@ inline int launch_adof(const KArgs& k, cudaStream_t s) {
     if (cudaMemsetAsync(k.scratch, 0, sizeof(unsigned int), s) != cudaSuccess) { cudaGetLastError(); return PPK_ERR_LAUNCH; }
   }
   const long long tiles = (k.n + kAdofTile - 1) / kAdofTile;
-  const long long blocks = (tiles + kAdofWarps - 1) / kAdofWarps;
-  adof_step_kernel<<<(unsigned)blocks, kAdofWarps * 32, smem, s>>>(k);
+  adof_step_kernel<<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
   if (cudaGetLastError() != cudaSuccess) return PPK_ERR_LAUNCH;
   if (fused_reset) return launch_adof_clear(k.scratch, k.flags, k.n, s);
   return PPK_OK;

@@ -146,7 +146,7 @@ int ppk_host_session_create(const PpkTask* task, int64_t max_envs, int32_t num_c
       d.paddle_body[h] = row < 0 ? 0 : row;
     }
   }
-  if (task->variant != PPK_ADOF && task->variant != PPK_BASE) ++next;   // pad row: keeps bulk staging windows in bounds
+  if (task->variant != PPK_BASE) ++next;   // pad row: keeps the bulk staging windows in bounds
   s->dev_bodies = next;
   d.num_bodies = next;
   const int A = task->num_actors, D = task->num_dofs;

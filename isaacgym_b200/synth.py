@@ -102,6 +102,14 @@ def make_state(cfg: TaskConfig, num_envs: int, seed: int = 0, device: str = "cpu
         p = cfg.paddle_body[k]
         rb[:, p, 0:3] = torch.where(near.unsqueeze(-1), root[:, ball_row, 0:3] + jitter, rb[:, p, 0:3])
 
+    if cfg.variant == "a3":
+        # A3 terminates an env as soon as the ball is behind the paddle (A3:1149,1160): keep that a
+        # ~5 % event, and launch reset balls beyond every paddle, so the batch is not one perpetual reset
+        p = cfg.paddle_body[0]
+        keep = torch.rand(n, generator=g, device=dev) < 0.95
+        ahead = torch.minimum(rb[:, p, 0], root[:, cfg.ball_actor, 0] - 0.01)
+        rb[:, p, 0] = torch.where(keep, ahead, rb[:, p, 0])
+
     dof_scale = 1.0
     if cfg.variant == "adof":
         dof_scale = 0.05
@@ -117,6 +125,8 @@ def make_state(cfg: TaskConfig, num_envs: int, seed: int = 0, device: str = "cpu
     # reset sources
     init_root = _rows(n, A, g, dev, pos_std=0.02)
     init_root[..., 7:13] = 0.0
+    if cfg.variant == "a3":
+        init_root[:, cfg.ball_actor, 0] += 3.7
     st["initial_root_states"] = init_root
     if cfg.variant == "adof":
         st["initial_dof_states"] = torch.zeros(n, D, 2, device=dev)            # ADOF:249
