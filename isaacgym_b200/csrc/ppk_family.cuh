@@ -194,6 +194,23 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       for (int i = 0; i < NF; ++i) flag[i] = k.flags[i][env] != 0;
     }
   }
+  // Time-out and ball-height termination are already decidable: pull the reset sources of those
+  // envs towards L2 now, so the predicated reset below does not pay a DRAM round trip.
+  if ((phases & PPK_PHASE_RESET) && lane_env) {
+    const bool timeout = prog + ((phases & PPK_PHASE_PROGRESS) ? 1 : 0) >= k.max_len - 1;
+    const bool low_ball = (V != PPK_NES) && (bz < 0.1f);
+    if (timeout || low_ball || reset_prev != 0) {
+      const char* ir = reinterpret_cast<const char*>(k.init_root + (size_t)env * L::kRootEnv);
+      prefetch_l2(ir);
+      prefetch_l2(ir + 4 * L::kRootEnv - 4);
+      prefetch_l2(k.reset_vel + (size_t)env * 3);
+      if (k.reset_dof) {
+        const char* id = reinterpret_cast<const char*>(k.init_dof + (size_t)env * 2 * D);
+        prefetch_l2(id);
+        prefetch_l2(id + 8 * D - 4);
+      }
+    }
+  }
   if (bulk) mbar_wait(bar, 0);
 
   const int le = (lane < TILE) ? lane : 0;     // smem row this lane reads (idle lanes read row 0)
