@@ -192,37 +192,28 @@ def time_steps(tasks, steps, warmup, with_pre, log_every, world, dist):
     return sec, steps * per_step
 
 
-def run_e2e(variant, n, steps, device):
+def run_e2e(variant, n, steps, device, chunks=4):
     """The same step through the host-buffer C-ABI session: state tensors in pinned HOST memory,
     H2D of the step's inputs and D2H of its results inside the timed region (wall clock: the call
     returns when the results are on the host)."""
-    from isaacgym_b200 import _native as N
     from isaacgym_b200.config import CONFIGS
+    from isaacgym_b200.host_session import HostSession
     from isaacgym_b200.synth import make_state
     cfg = CONFIGS[variant]
-    lib = N.load()
     st = make_state(cfg, n, seed=4242, device="cpu", adversarial=False)
-    if variant == "base":
-        st["reset_ball_vel"] = st["reset_ball_vel"][:2].contiguous()
-    st["pre_ball_states"] = st["pre_ball_states"][:, [7, 9]].contiguous()
-    host = {k: (v.pin_memory() if v.numel() > 0 else v) for k, v in st.items()}
-    hb = N.make_buffers(cfg, host, host=True)
-    sess = C.c_void_p()
-    N.check(lib.ppk_host_session_create(N.make_task(cfg), n, 8, C.byref(sess)), "host_session_create")
-    phases = N.PHASE_ALL & ~N.PHASE_STATS
+    sess = HostSession(cfg, st, num_chunks=chunks)
     try:
-        for _ in range(3):
-            N.check(lib.ppk_host_post_physics_step(sess, hb, phases), "host_step")
+        for _ in range(4):                      # eager, graph capture, two replays
+            sess.post_physics_step()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(steps):
-            N.check(lib.ppk_host_post_physics_step(sess, hb, phases), "host_step")
+            sess.post_physics_step()
         sec = time.perf_counter() - t0
-        h2d, d2h = C.c_int64(), C.c_int64()
-        lib.ppk_host_session_traffic(sess, C.byref(h2d), C.byref(d2h))
+        h2d, d2h = sess.traffic()
     finally:
-        lib.ppk_host_session_destroy(sess)
-    return sec, int(h2d.value), int(d2h.value)
+        sess.close()
+    return sec, h2d, d2h
 
 
 def run_cpu(variant, n, steps, warmup, threads):
@@ -257,7 +248,7 @@ def main():
     ap.add_argument("--workload", default="tilt", choices=sorted(WORKLOADS))
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--sets", type=int, default=8)
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-extras", action="store_true", help="skip other_workloads / e2e / cpu_baseline")
     args = ap.parse_args()
 

@@ -157,6 +157,11 @@ typedef struct PpkBuffers {
   double* stats;
   /* >= 64 bytes of device scratch, zeroed once by the caller (ADOF any-env-reset flag)    */
   uint32_t* scratch;
+  /* optional: where the predicated reset of ppk_post_physics_step writes the root / DOF rows of
+   * resetting envs (same shapes as root_states / dof_states).  NULL = in place.  The host session
+   * points them at the caller's pinned host tensors so only reset rows travel back over PCIe. */
+  float* root_states_out;
+  float* dof_states_out;
 } PpkBuffers;
 
 PPK_API int ppk_abi_version(void);

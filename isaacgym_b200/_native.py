@@ -48,6 +48,7 @@ class PpkBuffers(C.Structure):
         ("flags", C.c_void_p * PPK_MAX_FLAGS),
         ("actions", C.c_void_p), ("pd_action_offset", C.c_void_p), ("pd_action_scale", C.c_void_p),
         ("pd_targets", C.c_void_p), ("stats", C.c_void_p), ("scratch", C.c_void_p),
+        ("root_states_out", C.c_void_p), ("dof_states_out", C.c_void_p),
     ]
 
 

@@ -367,7 +367,7 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
   const bool do_reset = (phases & PPK_PHASE_RESET) && is_reset && lane_env;
   if (do_reset) {
     const float* ir = k.init_root + (size_t)env * 39;
-    float* gr = k.root + (size_t)env * 39;
+    float* gr = k.root_out + (size_t)env * 39;
     const float* rv = k.reset_vel + (size_t)env * 3;
     const float* ryz = k.reset_yz + (size_t)env * 2;
     for (int a = 0; a < 3; ++a) {
@@ -381,7 +381,7 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
     gr[k.ball * kRow + 1] = by; gr[k.ball * kRow + 2] = bz;
     gr[k.ball * kRow + 7] = bvx; gr[k.ball * kRow + 8] = bvy; gr[k.ball * kRow + 9] = bvz;
     if (k.reset_dof) {
-      float* gd = k.dof + (size_t)env * 2 * D;
+      float* gd = k.dof_out + (size_t)env * 2 * D;
       for (int i = 0; i < 2 * D; ++i) {
         float v = idof_s[le * L::kDof + i];
         dof_s[le * L::kDof + i] = v;

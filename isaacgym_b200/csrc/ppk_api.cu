@@ -23,6 +23,8 @@ int fill_args(const PpkTask* t, const PpkBuffers* b, uint32_t phases, KArgs* k) 
     return PPK_ERR_SHAPE;
   memset(k, 0, sizeof(*k));
   k->rb = b->rigid_body_states; k->root = b->root_states; k->dof = b->dof_states; k->force = b->dof_forces;
+  k->root_out = b->root_states_out ? b->root_states_out : b->root_states;
+  k->dof_out = b->dof_states_out ? b->dof_states_out : b->dof_states;
   k->pre = b->pre_ball_states; k->init_root = b->initial_root_states; k->init_dof = b->initial_dof_states;
   k->init_rb = b->initial_body_states; k->reset_vel = b->reset_ball_vel; k->reset_yz = b->reset_ball_pos_yz;
   k->obs = b->obs_buf; k->rew = b->rew_buf;

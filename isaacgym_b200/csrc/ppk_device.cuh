@@ -18,6 +18,8 @@ struct KArgs {
   const float* rb;
   float* root;
   float* dof;
+  float* root_out;   // where the predicated reset writes root / DOF rows (= root / dof unless the caller splits them)
+  float* dof_out;
   const float* force;
   const float* pre;
   const float* init_root;

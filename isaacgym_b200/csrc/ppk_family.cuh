@@ -283,7 +283,7 @@ family_step_kernel(const __grid_constant__ KArgs k) {
   const bool do_reset = (phases & PPK_PHASE_RESET) && is_reset && lane_env;
   if (do_reset) {
     const float* ir = k.init_root + (size_t)env * L::kRootEnv;
-    float* gr = k.root + (size_t)env * L::kRootEnv;
+    float* gr = k.root_out + (size_t)env * L::kRootEnv;
     const float* rv = k.reset_vel + (size_t)env * 3;
     float nvx = rv[0], nvy = rv[1], nvz = rv[2];
 #pragma unroll
@@ -298,7 +298,7 @@ family_step_kernel(const __grid_constant__ KArgs k) {
     bvx = nvx; bvy = nvy; bvz = nvz;
     if (k.reset_dof) {
       const float* id = k.init_dof + (size_t)env * 2 * D;
-      float* gd = k.dof + (size_t)env * 2 * D;
+      float* gd = k.dof_out + (size_t)env * 2 * D;
 #pragma unroll
       for (int i = 0; i < 2 * D; ++i) {
         const float v = id[i];

@@ -279,3 +279,33 @@ def test_stats_reduce_and_task_logging():
     assert abs(m["reward_sum"] - float(stats["reward_sum"]) / n) < 1e-6 * max(1.0, abs(float(stats["reward_sum"]) / n)) + 1e-6
     assert m["progress_sum"] == float(stats["progress_sum"]) / n
     assert float(task.stats.slots.abs().sum()) == 0.0      # slots are cleared by the reduce
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("pin", [True, False])
+def test_host_session_equals_device_path(variant, pin):
+    """ppk_host_post_physics_step (host tensors, chunked H2D/kernel/D2H pipeline; eager on the first
+    call, CUDA-graph capture on the second, replay afterwards) gives the same buffers as the device
+    path, step after step.  Pinned tensors take the zero-copy route for the small per-env buffers
+    and reset rows, pageable ones the all-DMA route."""
+    from isaacgym_b200.host_session import HostSession
+    cfg = CONFIGS[variant]
+    n = 3000                               # not a multiple of the chunk size: exercises tail tiles
+    st = make_state(cfg, n, seed=31)
+    if variant == "base":
+        st["reset_buf"] = (torch.rand(n, generator=torch.Generator().manual_seed(3)) < 0.1).to(torch.int64)
+        st["reset_ball_vel"] = st["reset_ball_vel"][:2].contiguous()
+    dev = gpu_state(st)
+    if variant != "base":
+        dev["pre_ball_states"] = dev["pre_ball_states"][:, [7, 9]].contiguous()
+    sess = HostSession(cfg, st, num_chunks=3, pin=pin)
+    try:
+        for step in range(4):
+            sess.post_physics_step(N.PHASE_ALL & ~N.PHASE_STATS)
+            run(cfg, dev, N.PHASE_ALL & ~N.PHASE_STATS)
+            for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names + cfg.counter_names:
+                assert torch.equal(sess.state[name], dev[name].cpu()), f"{variant} step {step}: {name}"
+        h2d, d2h = sess.traffic()
+        assert h2d > 0 and d2h > 0
+    finally:
+        sess.close()
