@@ -22,10 +22,11 @@
 
 namespace ppk {
 
-constexpr int kFamilyThreads = 96;
+// warps 1..OW rotate bodies, warp 0 does the reward; OW is chosen per variant (register budget)
 
-template <int H, int J, int D, int A, int TILE>
+template <int H, int J, int D, int A, int TILE, int OW>
 struct FamilyLayout {
+  static constexpr int kThreads = 32 * (1 + OW);
   static constexpr int kUnits = TILE * H;                               // (env, humanoid) pairs
   static constexpr int kSpanRows = J - 1;                               // rows ids[1..J)
   static constexpr int kSpanFloats = ((kSpanRows * kRow + 3 + 3) / 4) * 4;   // 120: run + alignment slack
@@ -45,18 +46,21 @@ struct FamilyLayout {
   static_assert((TILE * 2 * D) % 4 == 0 && (TILE * D) % 4 == 0, "16-byte bulk sizes");
   static_assert(kOffBar % 2 == 0, "mbarrier alignment");
   static_assert(3 * J <= 32, "one lane per output float of a body segment");
-  static_assert(kUnits % 2 == 0 && kUnits / 2 <= 32, "two obs warps, one heading per lane");
+  static_assert(kUnits % OW == 0 && kUnits / OW <= 32, "one heading per lane of an obs warp");
   static_assert(H * 6 <= D, "ball-in-frame scratch aliases the force staging");
 };
 
 // named barrier 1: obs warps arrive once their heading tables are written, warp 0 waits on it
-__device__ __forceinline__ void hdr_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(kFamilyThreads) : "memory"); }
-__device__ __forceinline__ void hdr_wait() { asm volatile("bar.sync 1, %0;" ::"n"(kFamilyThreads) : "memory"); }
+__device__ __forceinline__ void hdr_arrive(int threads) { asm volatile("bar.arrive 1, %0;" ::"r"(threads) : "memory"); }
+__device__ __forceinline__ void hdr_wait(int threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
 
-template <int V, int H, int J, int D, int A, int TILE>
-__global__ void __launch_bounds__(kFamilyThreads, 10)
+template <int V, int H, int J, int D, int A, int TILE, int OW>
+__global__ void __launch_bounds__(32 * (1 + OW), OW <= 2 ? 10 : 6)
 family_step_kernel(const __grid_constant__ KArgs k) {
-  using L = FamilyLayout<H, J, D, A, TILE>;
+  using L = FamilyLayout<H, J, D, A, TILE, OW>;
+  constexpr int kFamilyThreads = L::kThreads;
+  constexpr int kFamilyWarps = 1 + OW;
+  constexpr int kObsWarps = OW;
   extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -90,7 +94,7 @@ family_step_kernel(const __grid_constant__ KArgs k) {
     }
     // the 2 x kUnits row windows are issued by all three warps (the copy instruction takes
     // warp-uniform operands, so each warp serialises over its lanes)
-    for (int u = warp + 3 * lane; u < L::kUnits; u += 96) {
+    for (int u = warp + kFamilyWarps * lane; u < L::kUnits; u += kFamilyThreads) {
       const int e = u / H, h = u - e * H;
       const float* row = g_rb + (size_t)e * env_stride;
       const uintptr_t a1 = reinterpret_cast<uintptr_t>(row + k.ids[h][1] * kRow) & ~(uintptr_t)15;
@@ -120,8 +124,8 @@ family_step_kernel(const __grid_constant__ KArgs k) {
     if (!(phases & PPK_PHASE_OBS)) return;
     if (bulk) mbar_wait(bar, 0);
     // heading frames of this warp's units u = 2*lane + (warp-1)
-    if (lane < L::kUnits / 2) {
-      const int u = 2 * lane + (warp - 1);
+    if (lane < L::kUnits / kObsWarps) {
+      const int u = kObsWarps * lane + (warp - 1);
       const int e = u / H, h = u - e * H;
       int off0 = 0, off1 = 0;
       if (bulk) {   // where the row sits inside its 16-byte aligned staging window
@@ -137,7 +141,7 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       hd[3] = r0[0]; hd[4] = r0[1]; hd[5] = r0[2];
       hd[6] = __int_as_float(off0); hd[7] = __int_as_float(off1);
     }
-    hdr_arrive();       // warp 0 needs the frames for the ball
+    hdr_arrive(kFamilyThreads);       // warp 0 needs the frames for the ball
     __syncwarp();
     // lane = output float o of a 3J-float segment: body j = o/3, component c = o%3.
     //   out_c = v_c*a0 + ((s1*v_o)*m)*2 with (s1, o, m) = (-sz, y, cw) / (sz, x, cw) / (sz, z, sz)
@@ -149,7 +153,7 @@ family_step_kernel(const __grid_constant__ KArgs k) {
     const float sgn = (c == 0) ? -1.0f : 1.0f;
     float* g_obs = k.obs + (size_t)env0 * H * L::kObs;
 #pragma unroll 2
-    for (int u = warp - 1; u < L::kUnits; u += 2) {
+    for (int u = warp - 1; u < L::kUnits; u += kObsWarps) {
       const int e = u / H;
       const float* hd = hdr_s + u * L::kHdr;
       const float a0 = hd[0], sz = hd[1], cw = hd[2];
@@ -323,7 +327,7 @@ family_step_kernel(const __grid_constant__ KArgs k) {
   if (!(phases & PPK_PHASE_OBS)) return;
 
   // ---- ball in the heading frame (frames come from the obs warps) -------------------------------------
-  hdr_wait();
+  hdr_wait(kFamilyThreads);
   if (lane < TILE) {
 #pragma unroll
     for (int h = 0; h < H; ++h) {
