@@ -196,6 +196,17 @@ PPK_API int ppk_reset_idx(const PpkTask* task, const PpkBuffers* buf, const int6
  * pd_targets = offset + scale*actions; save the ball's pre-step velocity. */
 PPK_API int ppk_pre_physics_step(const PpkTask* task, const PpkBuffers* buf, void* stream);
 
+/* Device-side form of generate_random_speed_for_ball (TILT:307-318, NES:312-323, ADOF:357-367,
+ * A3:300-302) + the per-env host loop that calls it (TILT:857-862, ADOF:975-988): fills
+ * buf->reset_ball_vel [N,3] (and reset_ball_pos_yz [N,2] for ADOF) from a counter-based
+ * Philox4x32-10 stream keyed by `seed`, counter = (env_offset + n, epoch).  With
+ * refresh_consumed_only != 0 only the rows of envs whose reset_buf is set are redrawn (call it right
+ * after ppk_post_physics_step so every reset consumes a fresh draw).  Same ranges and formulas as the
+ * reference; parity with its Mersenne-Twister stream is statistical, not bitwise.  Not for BASE
+ * (one host-drawn velocity pair per reset_idx call, BASE:542). */
+PPK_API int ppk_sample_ball_launch(const PpkTask* task, const PpkBuffers* buf, uint64_t seed, uint64_t epoch,
+                                   int64_t env_offset, int32_t refresh_consumed_only, void* stream);
+
 /* Fold the stats slots into out[PPK_NUM_STATS] (device) and zero the slots. */
 PPK_API int ppk_stats_reduce(double* stats, double* out, void* stream);
 

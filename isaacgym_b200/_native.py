@@ -84,6 +84,9 @@ def load():
     lib.ppk_reset_idx.restype = C.c_int
     lib.ppk_reset_idx.argtypes = [C.POINTER(PpkTask), C.POINTER(PpkBuffers), C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ppk_sample_ball_launch.restype = C.c_int
+    lib.ppk_sample_ball_launch.argtypes = [C.POINTER(PpkTask), C.POINTER(PpkBuffers), C.c_uint64, C.c_uint64,
+                                           C.c_int64, C.c_int32, C.c_void_p]
     lib.ppk_stats_reduce.restype = C.c_int
     lib.ppk_stats_reduce.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     if hasattr(lib, "ppk_host_session_create"):

@@ -269,6 +269,23 @@ int ppk_pre_physics_step(const PpkTask* t, const PpkBuffers* b, void* stream) {
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 
+int ppk_sample_ball_launch(const PpkTask* t, const PpkBuffers* b, uint64_t seed, uint64_t epoch, int64_t env_offset,
+                           int32_t refresh_consumed_only, void* stream) {
+  if (t == nullptr || b == nullptr) return PPK_ERR_NULL;
+  if (t->struct_size != sizeof(PpkTask) || b->struct_size != sizeof(PpkBuffers)) return PPK_ERR_ABI;
+  if (t->variant <= PPK_BASE || t->variant > PPK_ADOF) return PPK_ERR_VARIANT;
+  if (b->num_envs < 0 || env_offset < 0) return PPK_ERR_SHAPE;
+  if (b->num_envs == 0) return PPK_OK;
+  if (!b->reset_ball_vel || (t->variant == PPK_ADOF && !b->reset_ball_pos_yz)) return PPK_ERR_NULL;
+  if (refresh_consumed_only && !b->reset_buf) return PPK_ERR_NULL;
+  const long long blocks = (b->num_envs + 255) / 256;
+  sample_launch_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      const_cast<float*>(b->reset_ball_vel), const_cast<float*>(b->reset_ball_pos_yz),
+      refresh_consumed_only ? reinterpret_cast<const long long*>(b->reset_buf) : nullptr, b->num_envs, t->variant,
+      (unsigned long long)seed, (unsigned long long)epoch, (long long)env_offset);
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+
 // Used by the host session: the shard-wide ADOF counter clear after all chunks ran (ADOF:1162-1175).
 int ppk_internal_adof_clear(const PpkBuffers* b, void* stream) {
   if (!b || !b->scratch) return PPK_ERR_NULL;

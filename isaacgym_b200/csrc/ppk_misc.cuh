@@ -184,6 +184,66 @@ __global__ void stats_reduce_kernel(double* stats, double* out) {
   out[s] = acc;
 }
 
+// ---- device-side ball launch sampler ------------------------------------------
+// The reference draws the launch velocity of every resetting env on the host with Python
+// `random.uniform` inside a per-env loop (TILT:857-862, generate_random_speed_for_ball TILT:307-318,
+// NES:312-323, ADOF:357-367, A3:300-302).  Here a counter-based Philox4x32-10 stream keyed by
+// (seed, env, epoch) fills the per-env launch table consumed by the predicated reset.  Same ranges
+// and formulas; bit parity with a Mersenne-Twister stream is impossible, so parity is statistical.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+__device__ __forceinline__ float u01(unsigned int x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }   // [0,1)
+
+__global__ void __launch_bounds__(256)
+sample_launch_kernel(float* __restrict__ vel, float* __restrict__ pos_yz, const long long* __restrict__ only_if_reset,
+                     long long n, int variant, unsigned long long seed, unsigned long long epoch, long long env_offset) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  if (only_if_reset != nullptr && only_if_reset[e] == 0) return;      // refresh only the rows just consumed
+  const unsigned long long g = (unsigned long long)(e + env_offset);  // global env id: shards draw disjoint streams
+  const uint4 r = philox4x32_10(make_uint4((unsigned)g, (unsigned)(g >> 32), (unsigned)epoch, (unsigned)(epoch >> 32)),
+                                make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  const float rad = 0.017453292519943295f;
+  float s, a, z = 0.0f, vx, vy, vz;
+  if (variant == PPK_TILT || variant == PPK_A4 || variant == PPK_ALIGN) {
+    // s = -U(8.0, 8.6 | 8.8), a = U(-5,5) deg, z = U(2,10) deg;  v = s*(cos a cos z, sin a sin z, sin a)
+    s = -(8.0f + u01(r.x) * (variant == PPK_ALIGN ? 0.8f : 0.6f));
+    a = (-5.0f + u01(r.y) * 10.0f) * rad;
+    z = (2.0f + u01(r.z) * 8.0f) * rad;
+    vx = s * cosf(a) * cosf(z); vy = s * sinf(a) * sinf(z); vz = s * sinf(a);
+  } else if (variant == PPK_NES || variant == PPK_ADOF) {
+    // v = (-s cos a cos z, s sin a cos z, s sin z)
+    const bool nes = variant == PPK_NES;
+    s = nes ? (5.4f + u01(r.x) * 0.5f) : (5.0f + u01(r.x) * 0.4f);
+    a = (nes ? (-5.0f + u01(r.y) * 10.0f) : (-8.0f + u01(r.y) * 11.0f)) * rad;
+    z = (nes ? (10.0f + u01(r.z) * 7.0f) : (14.0f + u01(r.z) * 10.0f)) * rad;
+    vx = -s * cosf(a) * cosf(z); vy = s * sinf(a) * cosf(z); vz = s * sinf(z);
+  } else {
+    // A3 / BASE: v = s*(cos a, sin a, 0), s = -U(6.5, 7.5)
+    s = -(6.5f + u01(r.x) * 1.0f);
+    a = (-5.0f + u01(r.y) * 10.0f) * rad;
+    vx = s * cosf(a); vy = s * sinf(a); vz = 0.0f;
+  }
+  vel[e * 3 + 0] = vx; vel[e * 3 + 1] = vy; vel[e * 3 + 2] = vz;
+  if (variant == PPK_ADOF && pos_yz != nullptr) {
+    // ADOF:127-128,976-979: ball y ~ U(-0.5, 0.1), z ~ U(0.96, 1.05); second Philox block
+    const uint4 q = philox4x32_10(make_uint4((unsigned)g, (unsigned)(g >> 32), (unsigned)epoch, (unsigned)(epoch >> 32) ^ 0x80000000u),
+                                  make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    pos_yz[e * 2 + 0] = -0.5f + u01(q.x) * 0.6f;
+    pos_yz[e * 2 + 1] = 0.96f + u01(q.y) * 0.09f;
+  }
+}
+
 // ADOF:1162-1175: when any env of the shard reset this step, all five counters are cleared.
 __global__ void __launch_bounds__(256)
 adof_clear_counters_kernel(const unsigned int* any_reset, unsigned char* c0, unsigned char* c1, unsigned char* c2,

@@ -138,6 +138,13 @@ class PingpongTask(VecTask):
                                         self._stream()), "ppk_reset_idx")
         return actor_out, dof_out
 
+    def sample_ball_launch(self, seed: int, epoch: int, env_offset: int = 0, refresh_consumed_only: bool = False):
+        """Device-side `generate_random_speed_for_ball` (TILT:307-318) for the whole shard: refills the
+        per-env launch table the predicated reset consumes (Philox4x32-10, counter = global env id, epoch)."""
+        N.check(self._lib.ppk_sample_ball_launch(self._task, self.buffers(), seed, epoch, env_offset,
+                                                 1 if refresh_consumed_only else 0, self._stream()),
+                "ppk_sample_ball_launch")
+
     def _log_now(self) -> bool:
         le = self.cfg.log_every
         return self.log_stats and le > 0 and self.num_steps % le == 0

@@ -168,8 +168,24 @@ def test_ragged_sizes(variant, n):
         st["reset_ball_vel"] = st["reset_ball_vel"][:1].repeat(2, 1).contiguous()
     want, _ = oracle_full_step(cfg, st)
     g = gpu_state(st)
-    # guard rows after the tensors: nothing beyond N may be written
+    # guard rows after the tensors: nothing beyond N may be written (compute-sanitizer is closed on
+    # this pool, so out-of-bounds stores are caught with sentinels instead)
+    guarded = {}
+    for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names + cfg.counter_names:
+        t = g[name]
+        big = torch.empty((n + 8,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        if t.dtype == torch.bool:
+            big[:] = True
+        else:
+            big.fill_(-777)
+        big[:n] = t
+        guarded[name] = big
+        g[name] = big[:n]
     run(cfg, g, N.PHASE_ALL)
+    for name, big in guarded.items():
+        tail = big[n:]
+        ok = bool(tail.all()) if big.dtype == torch.bool else bool((tail == -777).all())
+        assert ok, f"{variant} n={n}: {name} was written past its end"
     assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names, f"{variant} n={n}")
     assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], f"{variant} n={n}")
 
