@@ -23,7 +23,8 @@
 namespace ppk {
 
 constexpr int kAdofTile = 8;
-constexpr int kAdofThreads = 128;
+constexpr int kAdofObsWarps = 4;            // warps 1..4 reduce / rotate the balance bodies, two envs each
+constexpr int kAdofThreads = 32 * (1 + kAdofObsWarps);
 constexpr int kAdofD = 27;
 constexpr int kAdofJ = 10;       // ping-pong bodies
 constexpr int kAdofNB = 23;      // balance bodies
@@ -91,8 +92,10 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
   const float* g_init = k.init_rb + (size_t)env0 * env_stride;
 
   // position of env e's row 0 inside its 16-byte aligned staging window (floats)
+  const int off_rb0 = (int)((reinterpret_cast<uintptr_t>(g_rb) & 15u) >> 2);
+  const int off_init0 = (int)((reinterpret_cast<uintptr_t>(g_init) & 15u) >> 2);
   auto win_off = [&](const float* base, int e) -> int {
-    return bulk ? (int)((reinterpret_cast<uintptr_t>(base + (size_t)e * env_stride) & 15u) >> 2) : 0;
+    return bulk ? (((base == g_rb ? off_rb0 : off_init0) + e * env_stride) & 3) : 0;
   };
 
   // ---- stage -------------------------------------------------------------------------------
@@ -109,8 +112,8 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
       bulk_g2s(idof_s, k.init_dof + (size_t)env0 * L::kDof, 4u * T * L::kDof, bar);
       bulk_g2s(force_s, k.force + (size_t)env0 * D, 4u * T * D, bar);
     }
-    if (lane < 4) {       // 16 windows, four per warp
-      const int i = warp * 4 + lane;
+    if (warp >= 1 && lane < 4) {       // 16 windows, four per reducing warp
+      const int i = (warp - 1) * 4 + lane;
       const int e = i >> 1;
       if (i & 1) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(g_init + (size_t)e * env_stride) & ~(uintptr_t)15;
@@ -151,7 +154,7 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
     // heading frames of this warp's envs, computed once with lane = pass slot and broadcast per pass
     Heading my_hq; my_hq.sz = 0.0f; my_hq.cw = 1.0f;
     {
-      const int e = (warp - 1) + 3 * lane;
+      const int e = (warp - 1) + kAdofObsWarps * lane;
       if (e < T) {
         const float* r0 = rb_s + e * L::kSRb + win_off(g_rb, e) + pp_root * kRow;
         my_hq = heading_quat_inv(r0[3], r0[4], r0[5], r0[6]);
@@ -159,7 +162,7 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
     }
     int slot = 0;
 #pragma unroll 1
-    for (int e = warp - 1; e < T; e += 3, ++slot) {
+    for (int e = warp - 1; e < T; e += kAdofObsWarps, ++slot) {
       const float* rb_e = rb_s + e * L::kSRb + win_off(g_rb, e);
       const float* in_e = init_s + e * L::kSInit + win_off(g_init, e);
       const float* cur = rb_e + bal_id * kRow;
@@ -170,8 +173,9 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
       float dvx = ref[7] - cur[7], dvy = ref[8] - cur[8], dvz = ref[9] - cur[9];
       // has_fallen uses cur - ref (ADOF:1412)
       float nx = cur[0] - ref[0], ny = cur[1] - ref[1], nz = cur[2] - ref[2];
-      float s_dp2 = body_on ? (dpx * dpx + dpy * dpy + dpz * dpz) / 3.0f : 0.0f;
-      float s_dv2 = body_on ? (dvx * dvx + dvy * dvy + dvz * dvz) / 3.0f : 0.0f;
+      // per-body sums of squares; the /3 of the inner mean is applied once per env in phase R
+      float s_dp2 = body_on ? (dpx * dpx + dpy * dpy + dpz * dpz) : 0.0f;
+      float s_dv2 = body_on ? (dvx * dvx + dvy * dvy + dvz * dvz) : 0.0f;
       float s_nrm = body_on ? sqrtf(nx * nx + ny * ny + nz * nz) : 0.0f;
       // DOF terms, lane = DOF index
       const bool dof_on = lane < D;
@@ -183,8 +187,8 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
       float s_dq5 = (dof_on && lane >= 22) ? dq * dq : 0.0f;
       float s_dqd22 = (dof_on && lane < 22) ? dqd * dqd : 0.0f;
       float s_pow = dof_on ? fabsf(force_s[e * D + dl] * qd) : 0.0f;
-      s_dp2 = warp_sum(s_dp2); s_dv2 = warp_sum(s_dv2); s_nrm = warp_sum(s_nrm);
-      s_dq22 = warp_sum(s_dq22); s_dq5 = warp_sum(s_dq5); s_dqd22 = warp_sum(s_dqd22); s_pow = warp_sum(s_pow);
+      // all seven sums in one butterfly: lane L ends up with the total of value (L >> 2) & 7
+      const float red = warp_sum8(s_dp2, s_dv2, s_nrm, s_dq22, s_dq5, s_dqd22, s_pow, 0.0f, lane);
       // heading frames: ping-pong root body and balance root body (both row 0 in the shipped config)
       const float* r0 = rb_e + pp_root * kRow;
       Heading hq_pp;
@@ -192,12 +196,13 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
       hq_pp.cw = __shfl_sync(full, my_hq.cw, slot);
       const float* b0 = rb_e + bal_root * kRow;
       Heading hq_bal = (bal_root == pp_root) ? hq_pp : heading_quat_inv(b0[3], b0[4], b0[5], b0[6]);
-      if (lane == 0) {
+      {
         float* hd = hdr_s + e * L::kSHdr;
-        hd[H_A0] = 2.0f * (hq_pp.cw * hq_pp.cw) - 1.0f; hd[H_SZ] = hq_pp.sz; hd[H_CW] = hq_pp.cw;
-        hd[H_RX] = r0[0]; hd[H_RY] = r0[1]; hd[H_RZ] = r0[2];
-        hd[H_SUM_DP2] = s_dp2; hd[H_SUM_DV2] = s_dv2; hd[H_SUM_NORM] = s_nrm;
-        hd[H_SUM_DQ22] = s_dq22; hd[H_SUM_DQ5] = s_dq5; hd[H_SUM_DQD22] = s_dqd22; hd[H_POWER] = s_pow;
+        if ((lane & 3) == 0 && lane < 28) hd[H_SUM_DP2 + (lane >> 2)] = red;     // slots are consecutive
+        if (lane == 31) {
+          hd[H_A0] = 2.0f * (hq_pp.cw * hq_pp.cw) - 1.0f; hd[H_SZ] = hq_pp.sz; hd[H_CW] = hq_pp.cw;
+          hd[H_RX] = r0[0]; hd[H_RY] = r0[1]; hd[H_RZ] = r0[2];
+        }
       }
       if ((phases & PPK_PHASE_OBS) && e < nvalid) {
         // imitation observation segments [121,190) = 10*R(dP), [190,259) = R(dV)
@@ -290,8 +295,8 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
 
   if (phases & PPK_PHASE_REWARD) {
     // compute_imitation_reward, is_g1 branch (ADOF:1330-1418)
-    float r_body_pos = expf(-50.0f * (hd[H_SUM_DP2] / (float)NB));
-    float r_body_vel = expf(-4.0f * (hd[H_SUM_DV2] / (float)NB));
+    float r_body_pos = expf(-50.0f * ((hd[H_SUM_DP2] / 3.0f) / (float)NB));
+    float r_body_vel = expf(-4.0f * ((hd[H_SUM_DV2] / 3.0f) / (float)NB));
     float first22 = 10.0f * expf(-2500.0f * (hd[H_SUM_DQ22] / 22.0f));
     float last5 = 0.2f * expf(-5.0f * (hd[H_SUM_DQ5] / 5.0f));
     float r_dof_vel = expf(-0.05f * (hd[H_SUM_DQD22] / 22.0f));

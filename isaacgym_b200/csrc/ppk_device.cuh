@@ -64,6 +64,24 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Eight warp-wide sums for the price of ~one: each butterfly level halves the number of values a
+// lane carries.  Returns, in lane L, the total over all lanes of value number (L >> 2) & 7.
+__device__ __forceinline__ float warp_sum8(float v0, float v1, float v2, float v3, float v4, float v5, float v6,
+                                           float v7, int lane) {
+  const unsigned full = 0xffffffffu;
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float w0 = (b4 ? v4 : v0) + __shfl_xor_sync(full, b4 ? v0 : v4, 16);
+  float w1 = (b4 ? v5 : v1) + __shfl_xor_sync(full, b4 ? v1 : v5, 16);
+  float w2 = (b4 ? v6 : v2) + __shfl_xor_sync(full, b4 ? v2 : v6, 16);
+  float w3 = (b4 ? v7 : v3) + __shfl_xor_sync(full, b4 ? v3 : v7, 16);
+  float x0 = (b3 ? w2 : w0) + __shfl_xor_sync(full, b3 ? w0 : w2, 8);
+  float x1 = (b3 ? w3 : w1) + __shfl_xor_sync(full, b3 ? w1 : w3, 8);
+  float y = (b2 ? x1 : x0) + __shfl_xor_sync(full, b2 ? x0 : x1, 4);
+  y += __shfl_xor_sync(full, y, 2);
+  y += __shfl_xor_sync(full, y, 1);
+  return y;
+}
+
 // streaming loads/stores: every byte of state is touched once per step
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
@@ -83,10 +101,35 @@ __device__ __forceinline__ Heading heading_quat_inv(float qx, float qy, float qz
   float a0 = 2.0f * (qw * qw) - 1.0f;
   float rx = (a0 + 0.0f) + (qx * qx) * 2.0f;
   float ry = (0.0f + (qz * qw) * 2.0f) + (qy * qx) * 2.0f;
+#ifdef PPK_HALF_ANGLE_HEADING
+  // Experimental: sin/cos of -atan2(ry,rx)/2 from half-angle identities (no atan2f/sinf/cosf).
+  // Well conditioned on both half planes; differs from the faithful path by a few ulp.
+  float s, c;
+  {
+    const float r = sqrtf(rx * rx + ry * ry);
+    if (r == 0.0f) {
+      // atan2(+-0, +0) = +-0, atan2(+-0, -0) = +-pi
+      const bool neg_x = signbit(rx);
+      c = neg_x ? 0.0f : 1.0f;
+      s = neg_x ? (signbit(ry) ? 1.0f : -1.0f) : 0.0f;
+    } else {
+      const float ch = rx / r, sh = ry / r;
+      if (rx >= 0.0f) {
+        c = sqrtf((1.0f + ch) * 0.5f);
+        s = -(sh / (2.0f * c));
+      } else {
+        const float s2 = copysignf(sqrtf((1.0f - ch) * 0.5f), ry);
+        c = sh / (2.0f * s2);
+        s = -s2;
+      }
+    }
+  }
+#else
   float heading = atan2f(ry, rx);
   float half = (-heading) / 2.0f;
   float s = sinf(half);
   float c = cosf(half);
+#endif
   float nrm = sqrtf(s * s + c * c);
   nrm = fmaxf(nrm, 1e-9f);
   Heading h;
