@@ -73,3 +73,34 @@ def test_sampler_is_counter_based():
     torch.cuda.synchronize()
     changed = (a.st["reset_ball_vel"] != before).any(dim=1)
     assert torch.equal(changed, a.reset_buf.bool())
+
+
+@pytest.mark.parametrize("variant", ["tilt", "a4", "adof"])
+def test_unaligned_shard_takes_the_generic_path(variant):
+    """A shard that starts at an odd env of a larger allocation is only 8-byte aligned: bulk async
+    staging is illegal there (KArgs.bulk_ok = 0) and every tile goes through the LDG path.  Results
+    must be identical to the aligned (bulk) run on the same envs."""
+    from isaacgym_b200 import _native as N
+    cfg = CONFIGS[variant]
+    n = 1024
+    st = make_state(cfg, n + 1, seed=8, adversarial=False)
+    lib = N.load()
+
+    def step(state):
+        g = {k: v.to(DEV) for k, v in state.items()}
+        g["stats"] = torch.zeros(N.PPK_STATS_SLOTS, N.PPK_NUM_STATS, dtype=torch.float64, device=DEV)
+        g["scratch"] = torch.zeros(16, dtype=torch.int32, device=DEV)
+        return g
+
+    big = step(st)
+    # shard A: envs 1..n as views into the big tensors (misaligned start)
+    view = {k: (v[1:] if (v.dim() > 0 and v.shape[0] == n + 1) else v) for k, v in big.items()}
+    assert view["rigid_body_states"].data_ptr() % 16 != 0
+    # shard B: the same envs, freshly allocated (aligned)
+    copy = {k: (v[1:].clone() if (v.dim() > 0 and v.shape[0] == n + 1) else v.clone()) for k, v in big.items()}
+    for g in (view, copy):
+        g["progress_buf"] = g["progress_buf"].clone()      # int64 views at odd offsets are still 8-byte aligned
+        N.check(lib.ppk_post_physics_step(N.make_task(cfg), N.make_buffers(cfg, g), N.PHASE_ALL, N.current_stream_ptr()), "step")
+    torch.cuda.synchronize()
+    for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names + cfg.counter_names:
+        assert torch.equal(view[name], copy[name]), name
