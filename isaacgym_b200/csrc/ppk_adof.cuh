@@ -475,8 +475,6 @@ inline int launch_adof(const KArgs& k0, cudaStream_t s) {
   }
   const bool fused_reset = (k.phases & PPK_PHASE_RESET) != 0 && !(k.phases & kPhaseDeferCounterClear);
   if (fused_reset) {
-    for (int i = 4; i < 9; ++i)
-      if (reinterpret_cast<uintptr_t>(k.flags[i]) & 3u) return PPK_ERR_ALIGN;
     if (cudaMemsetAsync(k.scratch, 0, sizeof(unsigned int), s) != cudaSuccess) { cudaGetLastError(); return PPK_ERR_LAUNCH; }
   }
   const long long tiles = (k.n + kAdofTile - 1) / kAdofTile;

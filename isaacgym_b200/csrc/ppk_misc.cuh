@@ -249,8 +249,16 @@ __global__ void __launch_bounds__(256)
 adof_clear_counters_kernel(const unsigned int* any_reset, unsigned char* c0, unsigned char* c1, unsigned char* c2,
                            unsigned char* c3, unsigned char* c4, long long n) {
   if (*any_reset == 0u) return;
-  const long long words = (n + 3) / 4;    // tensors are at least 4-byte aligned allocations; tail handled bytewise
   const long long stride = (long long)gridDim.x * blockDim.x;
+  const uintptr_t all = reinterpret_cast<uintptr_t>(c0) | reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(c2) |
+                        reinterpret_cast<uintptr_t>(c3) | reinterpret_cast<uintptr_t>(c4);
+  if (all & 3u) {     // a shard view at an odd env offset: clear bytewise
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+      c0[j] = 0; c1[j] = 0; c2[j] = 0; c3[j] = 0; c4[j] = 0;
+    }
+    return;
+  }
+  const long long words = (n + 3) / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) {
     long long b = i * 4;
     if (b + 4 <= n) {
