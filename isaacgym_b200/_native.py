@@ -56,7 +56,8 @@ _LIB = None
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libppk.so")
+    # PPK_LIB: load another build of the same ABI (A/B measurements of kernel variants)
+    return os.environ.get("PPK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libppk.so")
 
 
 def load():

@@ -294,6 +294,13 @@ int ppk_internal_adof_clear(const PpkBuffers* b, void* stream) {
   return launch_adof_clear(b->scratch, b->flags, b->num_envs, static_cast<cudaStream_t>(stream));
 }
 
+#ifdef PPK_TRACE
+// debug builds only (-DPPK_TRACE): device buffer of >= blocks*8*4 uint64 receiving timeline stamps
+PPK_API int ppk_debug_set_trace(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(ppk::g_trace, &buf, sizeof(buf)) == cudaSuccess ? PPK_OK : PPK_ERR_CUDA;
+}
+#endif
+
 int ppk_stats_reduce(double* stats, double* out, void* stream) {
   if (!stats || !out) return PPK_ERR_NULL;
   stats_reduce_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(stats, out);

@@ -22,6 +22,21 @@
 
 namespace ppk {
 
+#ifdef PPK_TRACE
+// Debug build only: per-warp timeline stamps (globaltimer ns) -> g_trace[(block*8 + warp)*4 + slot]
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ void trace_stamp(int warp, int slot) {
+  if (g_trace != nullptr && (threadIdx.x & 31) == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[((size_t)blockIdx.x * 8 + warp) * 4 + slot] = t;
+  }
+}
+#define PPK_STAMP(slot) trace_stamp(warp, slot)
+#else
+#define PPK_STAMP(slot)
+#endif
+
 // warps 1..OW rotate bodies, warp 0 does the reward; OW is chosen per variant (register budget)
 
 template <int H, int J, int D, int A, int TILE, int OW>
@@ -30,19 +45,18 @@ struct FamilyLayout {
   static constexpr int kUnits = TILE * H;                               // (env, humanoid) pairs
   static constexpr int kSpanRows = J - 1;                               // rows ids[1..J)
   static constexpr int kSpanFloats = ((kSpanRows * kRow + 3 + 3) / 4) * 4;   // 120: run + alignment slack
-  static constexpr int kRow0Floats = 16;                                // 10 used floats + slack
   static constexpr int kRootEnv = A * kRow;
   static constexpr int kTail = 2 * D + 6;              // dof_pos, 0.1*dof_vel, ball local pos, vel
   static constexpr int kObs = 6 * J + kTail;           // 80 (D=7) / 94 (D=14)
-  static constexpr int kHdr = 8;                       // a0, sz, cw, root pos (3), window offsets (2)
+  static constexpr int kHdr = 16;                      // a0, sz, cw, span offset, then row ids[0]: pos3 quat4 vel3
+  static constexpr int kHdrRow = 4;                    // where the copy of row ids[0] starts inside a header
   // float offsets inside the CTA's shared memory
-  static constexpr int kOffRow0 = kUnits * kSpanFloats;
-  static constexpr int kOffDof = kOffRow0 + kUnits * kRow0Floats;
+  static constexpr int kOffDof = kUnits * kSpanFloats;
   static constexpr int kOffForce = kOffDof + TILE * 2 * D;
   static constexpr int kOffHdr = kOffForce + TILE * D;
   static constexpr int kOffBar = kOffHdr + kUnits * kHdr;            // 8-byte mbarrier
   static constexpr int kFloats = kOffBar + 4;
-  static constexpr uint32_t kTxBytes = 4u * (kUnits * (kSpanFloats + kRow0Floats) + TILE * 2 * D + TILE * D);
+  static constexpr uint32_t kTxBytes = 4u * (kUnits * kSpanFloats + TILE * 2 * D + TILE * D);
   static_assert((TILE * 2 * D) % 4 == 0 && (TILE * D) % 4 == 0, "16-byte bulk sizes");
   static_assert(kOffBar % 2 == 0, "mbarrier alignment");
   static_assert(3 * J <= 32, "one lane per output float of a body segment");
@@ -68,7 +82,6 @@ family_step_kernel(const __grid_constant__ KArgs k) {
   const int nvalid = (int)min((long long)TILE, k.n - env0);
 
   float* span_s = smem;
-  float* row0_s = smem + L::kOffRow0;
   float* dof_s = smem + L::kOffDof;
   float* force_s = smem + L::kOffForce;
   float* hdr_s = smem + L::kOffHdr;
@@ -81,6 +94,7 @@ family_step_kernel(const __grid_constant__ KArgs k) {
   const float* g_rb = k.rb + (size_t)env0 * env_stride;
 
   // ---- stage ---------------------------------------------------------------------------------------
+  PPK_STAMP(0);
   if (bulk) {
     if (threadIdx.x == 0) {
       mbar_init(bar, 1);
@@ -92,15 +106,17 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       bulk_g2s(dof_s, k.dof + (size_t)env0 * 2 * D, 4u * TILE * 2 * D, bar);
       bulk_g2s(force_s, k.force + (size_t)env0 * D, 4u * TILE * D, bar);
     }
-    // the 2 x kUnits row windows are issued by all three warps (the copy instruction takes
-    // warp-uniform operands, so each warp serialises over its lanes)
-    for (int u = warp + kFamilyWarps * lane; u < L::kUnits; u += kFamilyThreads) {
+    // The 2 x kUnits row windows: every warp walks its share of the units with warp-uniform
+    // addresses and one elected lane issues the copies (the copy instruction takes uniform operands;
+    // letting each lane issue its own makes the compiler serialise over the lanes at ~16
+    // instructions per copy).
+    const int wu = __shfl_sync(0xffffffffu, warp, 0);       // provably warp-uniform
+#pragma unroll 2
+    for (int u = wu; u < L::kUnits; u += kFamilyWarps) {
       const int e = u / H, h = u - e * H;
       const float* row = g_rb + (size_t)e * env_stride;
       const uintptr_t a1 = reinterpret_cast<uintptr_t>(row + k.ids[h][1] * kRow) & ~(uintptr_t)15;
-      const uintptr_t a0 = reinterpret_cast<uintptr_t>(row + k.ids[h][0] * kRow) & ~(uintptr_t)15;
-      bulk_g2s(span_s + u * L::kSpanFloats, reinterpret_cast<const void*>(a1), 4u * L::kSpanFloats, bar);
-      bulk_g2s(row0_s + u * L::kRow0Floats, reinterpret_cast<const void*>(a0), 4u * L::kRow0Floats, bar);
+      if (elect_one()) bulk_g2s(span_s + u * L::kSpanFloats, reinterpret_cast<const void*>(a1), 4u * L::kSpanFloats, bar);
     }
   } else {
     // generic path (tail tile, unaligned tensors, non-consecutive ids): plain loads, same layout
@@ -109,7 +125,7 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       const int e = u / H, h = u - e * H;
       const int j = r / kRow, c = r - j * kRow;
       float v = (e < nvalid) ? g_rb[(size_t)e * env_stride + k.ids[h][j] * kRow + c] : 0.0f;
-      if (j == 0) row0_s[u * L::kRow0Floats + c] = v;
+      if (j == 0) { if (c < 10) hdr_s[u * L::kHdr + L::kHdrRow + c] = v; }
       else span_s[u * L::kSpanFloats + (j - 1) * kRow + c] = v;
     }
     for (int f = threadIdx.x; f < TILE * 2 * D; f += kFamilyThreads)
@@ -119,27 +135,41 @@ family_step_kernel(const __grid_constant__ KArgs k) {
     __syncthreads();
   }
 
+  PPK_STAMP(1);
   if (warp != 0) {
     // ================= warps 1, 2: body observations =============================================
     if (!(phases & PPK_PHASE_OBS)) return;
+    // Row ids[0] (the heading / root body: 10 floats) is one plain load per float by the lane that
+    // owns the unit's frame, issued before the wait so it overlaps the bulk copies; a second TMA
+    // window per env would double the number of copy descriptors for 40 useful bytes.
+    const bool frame_lane = lane < L::kUnits / kObsWarps;
+    const int fu = kObsWarps * (frame_lane ? lane : 0) + (warp - 1);
+    float r0[10];
+    if (bulk && frame_lane) {
+      const int e = fu / H, h = fu - e * H;
+      const float* g0 = g_rb + (size_t)e * env_stride + k.ids[h][0] * kRow;
+#pragma unroll
+      for (int c = 0; c < 10; ++c) r0[c] = ld_stream(g0 + c);
+    }
     if (bulk) mbar_wait(bar, 0);
-    // heading frames of this warp's units u = 2*lane + (warp-1)
-    if (lane < L::kUnits / kObsWarps) {
-      const int u = kObsWarps * lane + (warp - 1);
-      const int e = u / H, h = u - e * H;
-      int off0 = 0, off1 = 0;
-      if (bulk) {   // where the row sits inside its 16-byte aligned staging window
-        const float* row = g_rb + (size_t)e * env_stride;
-        off0 = (int)((reinterpret_cast<uintptr_t>(row + k.ids[h][0] * kRow) & 15u) >> 2);
-        off1 = (int)((reinterpret_cast<uintptr_t>(row + k.ids[h][1] * kRow) & 15u) >> 2);
+    PPK_STAMP(2);
+    // heading frames of this warp's units u = OW*lane + (warp-1)
+    if (frame_lane) {
+      const int e = fu / H, h = fu - e * H;
+      float* hd = hdr_s + fu * L::kHdr;
+      int off1 = 0;
+      if (bulk) {   // where the run sits inside its 16-byte aligned staging window
+        off1 = (int)((reinterpret_cast<uintptr_t>(g_rb + (size_t)e * env_stride + k.ids[h][1] * kRow) & 15u) >> 2);
+#pragma unroll
+        for (int c = 0; c < 10; ++c) hd[L::kHdrRow + c] = r0[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 10; ++c) r0[c] = hd[L::kHdrRow + c];     // staged by the generic path
       }
-      const float* r0 = row0_s + u * L::kRow0Floats + off0;
       Heading hq = heading_quat_inv(r0[3], r0[4], r0[5], r0[6]);
-      float* hd = hdr_s + u * L::kHdr;
       hd[0] = 2.0f * (hq.cw * hq.cw) - 1.0f;
       hd[1] = hq.sz; hd[2] = hq.cw;
-      hd[3] = r0[0]; hd[4] = r0[1]; hd[5] = r0[2];
-      hd[6] = __int_as_float(off0); hd[7] = __int_as_float(off1);
+      hd[3] = __int_as_float(off1);
     }
     hdr_arrive(kFamilyThreads);       // warp 0 needs the frames for the ball
     __syncwarp();
@@ -158,9 +188,9 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       const float* hd = hdr_s + u * L::kHdr;
       const float a0 = hd[0], sz = hd[1], cw = hd[2];
       const float s1 = sgn * sz, m = (c == 2) ? sz : cw;
-      const float* row = (j == 0) ? (row0_s + u * L::kRow0Floats + __float_as_int(hd[6]))
-                                  : (span_s + u * L::kSpanFloats + __float_as_int(hd[7]) + (j - 1) * kRow);
-      const float pc = row[c] - hd[3 + c], po = row[oth] - hd[3 + oth];
+      const float* row = (j == 0) ? (hd + L::kHdrRow)
+                                  : (span_s + u * L::kSpanFloats + __float_as_int(hd[3]) + (j - 1) * kRow);
+      const float pc = row[c] - hd[L::kHdrRow + c], po = row[oth] - hd[L::kHdrRow + oth];
       const float out_p = pc * a0 + ((s1 * po) * m) * 2.0f;
       const float out_v = row[7 + c] * a0 + ((s1 * row[7 + oth]) * m) * 2.0f;
       if (lane_on && e < nvalid) {
@@ -169,6 +199,7 @@ family_step_kernel(const __grid_constant__ KArgs k) {
         st_stream(orow + 3 * J + o, out_v);
       }
     }
+    PPK_STAMP(3);
     return;
   }
 
@@ -216,6 +247,7 @@ family_step_kernel(const __grid_constant__ KArgs k) {
     }
   }
   if (bulk) mbar_wait(bar, 0);
+  PPK_STAMP(2);
 
   const int le = (lane < TILE) ? lane : 0;     // smem row this lane reads (idle lanes read row 0)
   float dofv[2 * D];
@@ -241,11 +273,10 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       const int pj = k.paddle_j[h];
       const int u = le * H + h;
       const float* pd;
-      if (pj >= 0) {
-        const int id = k.ids[h][pj > 0 ? 1 : 0];
-        const int off = bulk ? (int)((reinterpret_cast<uintptr_t>(g_rb + (size_t)le * env_stride + id * kRow) & 15u) >> 2) : 0;
-        pd = (pj == 0) ? (row0_s + u * L::kRow0Floats + off) : (span_s + u * L::kSpanFloats + off + (pj - 1) * kRow);
-      } else {
+      if (pj > 0) {
+        const int off = bulk ? (int)((reinterpret_cast<uintptr_t>(g_rb + (size_t)le * env_stride + k.ids[h][1] * kRow) & 15u) >> 2) : 0;
+        pd = span_s + u * L::kSpanFloats + off + (pj - 1) * kRow;
+      } else {    // paddle is the root body or not among the observation bodies: read it in place
         pd = k.rb + ((size_t)env * k.B + k.paddle_body[h]) * kRow;
       }
       s.px = pd[0]; s.py = pd[1]; s.pz = pd[2];
@@ -333,7 +364,7 @@ family_step_kernel(const __grid_constant__ KArgs k) {
     for (int h = 0; h < H; ++h) {
       const float* hd = hdr_s + (le * H + h) * L::kHdr;
       const float a0 = hd[0], sz = hd[1], cw = hd[2];
-      const float rx = bx - hd[3], ry = by - hd[4], rz = bz - hd[5];
+      const float rx = bx - hd[L::kHdrRow], ry = by - hd[L::kHdrRow + 1], rz = bz - hd[L::kHdrRow + 2];
       float* bs = ball_s + (le * H + h) * 6;
       bs[0] = rx * a0 + ((-(sz * ry)) * cw) * 2.0f;
       bs[1] = ry * a0 + ((sz * rx) * cw) * 2.0f;
@@ -357,6 +388,7 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       if (e < nvalid) st_stream(g_obs + (size_t)u * L::kObs + l, v);
     }
   }
+  PPK_STAMP(3);
 }
 
 }  // namespace ppk
