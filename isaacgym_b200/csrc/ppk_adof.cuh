@@ -67,7 +67,7 @@ __device__ __forceinline__ void adof_wait() { asm volatile("bar.sync 2, %0;" ::"
 
 constexpr uint32_t kPhaseDeferCounterClear = 1u << 8;   // internal (host session): clear counters once per shard
 
-__global__ void __launch_bounds__(kAdofThreads, 6)
+__global__ void __launch_bounds__(kAdofThreads, kAdofThreads <= 96 ? 10 : 6)
 adof_step_kernel(const __grid_constant__ KArgs k) {
   using L = AdofLayout;
   extern __shared__ __align__(128) float smem[];
@@ -112,15 +112,17 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
       bulk_g2s(idof_s, k.init_dof + (size_t)env0 * L::kDof, 4u * T * L::kDof, bar);
       bulk_g2s(force_s, k.force + (size_t)env0 * D, 4u * T * D, bar);
     }
-    if (warp >= 1 && lane < 4) {       // 16 windows, four per reducing warp
-      const int i = (warp - 1) * 4 + lane;
-      const int e = i >> 1;
-      if (i & 1) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(g_init + (size_t)e * env_stride) & ~(uintptr_t)15;
-        bulk_g2s(init_s + e * L::kSInit, reinterpret_cast<const void*>(a), 4u * L::kSInit, bar);
-      } else {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(g_rb + (size_t)e * env_stride) & ~(uintptr_t)15;
-        bulk_g2s(rb_s + e * L::kSRb, reinterpret_cast<const void*>(a), 4u * L::kSRb, bar);
+    if (warp >= 1) {       // 16 windows, four per reducing warp: warp-uniform addresses, one elected lane issues
+      const int wu = __shfl_sync(0xffffffffu, warp, 0);
+#pragma unroll
+      for (int q = 0; q < T / kAdofObsWarps; ++q) {
+        const int e = (wu - 1) * (T / kAdofObsWarps) + q;
+        const uintptr_t a_rb = reinterpret_cast<uintptr_t>(g_rb + (size_t)e * env_stride) & ~(uintptr_t)15;
+        const uintptr_t a_in = reinterpret_cast<uintptr_t>(g_init + (size_t)e * env_stride) & ~(uintptr_t)15;
+        if (elect_one()) {
+          bulk_g2s(rb_s + e * L::kSRb, reinterpret_cast<const void*>(a_rb), 4u * L::kSRb, bar);
+          bulk_g2s(init_s + e * L::kSInit, reinterpret_cast<const void*>(a_in), 4u * L::kSInit, bar);
+        }
       }
     }
   } else {

@@ -184,13 +184,13 @@ int ppk_post_physics_step(const PpkTask* t, const PpkBuffers* b, uint32_t phases
     case PPK_NES:
     case PPK_ALIGN:
       if (t->num_actors != 3 || t->num_dofs != 7 || t->num_body_ids != 10) return PPK_ERR_SHAPE;
-      if (t->variant == PPK_A3) return launch_family<PPK_A3, 1, 10, 7, 3, 32, 4>(k, s);
-      if (t->variant == PPK_TILT) return launch_family<PPK_TILT, 1, 10, 7, 3, 32, 4>(k, s);
-      if (t->variant == PPK_NES) return launch_family<PPK_NES, 1, 10, 7, 3, 32, 4>(k, s);
-      return launch_family<PPK_ALIGN, 1, 10, 7, 3, 32, 4>(k, s);
+      if (t->variant == PPK_A3) return launch_family<PPK_A3, 1, 10, 7, 3, 16, 2>(k, s);
+      if (t->variant == PPK_TILT) return launch_family<PPK_TILT, 1, 10, 7, 3, 16, 2>(k, s);
+      if (t->variant == PPK_NES) return launch_family<PPK_NES, 1, 10, 7, 3, 16, 2>(k, s);
+      return launch_family<PPK_ALIGN, 1, 10, 7, 3, 16, 2>(k, s);
     case PPK_A4:
       if (t->num_actors != 4 || t->num_dofs != 14 || t->num_body_ids != 10) return PPK_ERR_SHAPE;
-      return launch_family<PPK_A4, 2, 10, 14, 4, 16, 2>(k, s);
+      return launch_family<PPK_A4, 2, 10, 14, 4, 8, 1>(k, s);
     case PPK_ADOF:
       if (t->num_actors != 3 || t->num_dofs != 27 || t->num_body_ids != 10 || t->num_balance_ids != 23) return PPK_ERR_SHAPE;
       return launch_adof(k, s);
