@@ -149,7 +149,7 @@ typedef struct PpkBuffers {
    *        6 cross_net_count 7 hit_table_count 8 fall_down_count (ADOF:279-293)             */
   uint8_t* flags[PPK_MAX_FLAGS];
   /* pre_physics_step */
-  const float* actions;                 /* [N,D]                                             */
+  float* actions;                       /* [N,D] (clamped in place when clip_actions > 0)    */
   const float* pd_action_offset;        /* [D] TILT:666                                      */
   const float* pd_action_scale;         /* [D] TILT:667                                      */
   float* pd_targets;                    /* [N,D] written                                     */
@@ -162,6 +162,26 @@ typedef struct PpkBuffers {
    * points them at the caller's pinned host tensors so only reset rows travel back over PCIe. */
   float* root_states_out;
   float* dof_states_out;
+  /* ---- VecTask.step envelope, all optional ---------------------------------
+   * clip_actions > 0: ppk_pre_physics_step clamps `actions` to +-clip_actions in place before
+   *   scaling them (upstream VecTask.step clamps before calling pre_physics_step; clipActions
+   *   cfg/task/HumanoidPingpongTiltG1.yaml:26).
+   * timeout_buf [N] int64: 1 where the env's episode ran out this step (progress >= L-1 before
+   *   the reset cleared it) -- what RL libraries need to bootstrap truncated episodes.
+   * reset_count / reset_actor_indices / reset_dof_indices: the fused step appends, for every env
+   *   it resets, the rows `actor_indices.view(N,A)[env]` and `dof_indices.view(N,dof_per_env)[env]`
+   *   as int32 (TILT:876-877) -- the lists gym.set_actor_root_state_tensor_indexed /
+   *   set_dof_state_tensor_indexed take (TILT:881-888) -- and counts the envs in *reset_count, which
+   *   ppk_pre_physics_step zeroes (callers that skip the pre-step zero it themselves).  Env order
+   *   within the lists is unspecified. */
+  float clip_actions;
+  int32_t dof_indices_per_env;
+  int64_t* timeout_buf;
+  const int64_t* actor_indices;         /* [N*A]   TILT:645                                   */
+  const int64_t* dof_indices;           /* [N*dof_indices_per_env] TILT:646, A4:889           */
+  int32_t* reset_count;                 /* [1] device                                         */
+  int32_t* reset_actor_indices;         /* [N*A] capacity                                     */
+  int32_t* reset_dof_indices;           /* [N*dof_indices_per_env] capacity                   */
 } PpkBuffers;
 
 PPK_API int ppk_abi_version(void);

@@ -49,6 +49,9 @@ class PpkBuffers(C.Structure):
         ("actions", C.c_void_p), ("pd_action_offset", C.c_void_p), ("pd_action_scale", C.c_void_p),
         ("pd_targets", C.c_void_p), ("stats", C.c_void_p), ("scratch", C.c_void_p),
         ("root_states_out", C.c_void_p), ("dof_states_out", C.c_void_p),
+        ("clip_actions", C.c_float), ("dof_indices_per_env", C.c_int32), ("timeout_buf", C.c_void_p),
+        ("actor_indices", C.c_void_p), ("dof_indices", C.c_void_p), ("reset_count", C.c_void_p),
+        ("reset_actor_indices", C.c_void_p), ("reset_dof_indices", C.c_void_p),
     ]
 
 
@@ -201,6 +204,17 @@ def make_buffers(cfg: TaskConfig, st: dict, host: bool = False) -> PpkBuffers:
     b.pd_targets = get("pd_targets", f32, (n, D))
     b.stats = _ptr(st.get("stats"), torch.float64, "stats", host)
     b.scratch = _ptr(st.get("scratch"), torch.int32, "scratch", host)
+    # optional VecTask.step envelope outputs
+    b.clip_actions = float(st.get("clip_actions", 0.0) or 0.0)
+    b.timeout_buf = _ptr(st.get("timeout_buf"), i64, "timeout_buf", host)
+    if st.get("reset_count") is not None:
+        ai, di = st["actor_indices"], st["dof_indices"]
+        b.actor_indices = _ptr(ai, i64, "actor_indices", host)
+        b.dof_indices = _ptr(di, i64, "dof_indices", host)
+        b.dof_indices_per_env = di.numel() // max(n, 1)
+        b.reset_count = _ptr(st["reset_count"], torch.int32, "reset_count", host)
+        b.reset_actor_indices = _ptr(st["reset_actor_indices"], torch.int32, "reset_actor_indices", host)
+        b.reset_dof_indices = _ptr(st["reset_dof_indices"], torch.int32, "reset_dof_indices", host)
     return b
 
 

@@ -372,6 +372,9 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
 
   // ---- predicated reset (ADOF:965-1028) ----------------------------------------------------------
   const bool do_reset = (phases & PPK_PHASE_RESET) && is_reset && lane_env;
+  if (phases & PPK_PHASE_RESET) append_reset_indices(k, do_reset, env, lane);
+  if (k.timeout != nullptr && lane_env && (phases & (PPK_PHASE_REWARD | PPK_PHASE_PROGRESS)))
+    k.timeout[env] = (p_new >= k.max_len - 1) ? 1 : 0;
   if (do_reset) {
     const float* ir = k.init_root + (size_t)env * 39;
     float* gr = k.root_out + (size_t)env * 39;

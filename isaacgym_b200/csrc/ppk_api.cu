@@ -23,6 +23,18 @@ int fill_args(const PpkTask* t, const PpkBuffers* b, uint32_t phases, KArgs* k) 
     return PPK_ERR_SHAPE;
   memset(k, 0, sizeof(*k));
   k->rb = b->rigid_body_states; k->root = b->root_states; k->dof = b->dof_states; k->force = b->dof_forces;
+  k->timeout = reinterpret_cast<long long*>(b->timeout_buf);
+  if (b->reset_count != nullptr) {
+    if (!b->actor_indices || !b->reset_actor_indices || b->dof_indices_per_env < 0 ||
+        (b->dof_indices_per_env > 0 && (!b->dof_indices || !b->reset_dof_indices)))
+      return PPK_ERR_NULL;
+    k->actor_idx = reinterpret_cast<const long long*>(b->actor_indices);
+    k->dof_idx = reinterpret_cast<const long long*>(b->dof_indices);
+    k->dof_per_env = b->dof_indices_per_env;
+    k->reset_count = b->reset_count;
+    k->reset_actor_out = b->reset_actor_indices;
+    k->reset_dof_out = b->reset_dof_indices;
+  }
   k->root_out = b->root_states_out ? b->root_states_out : b->root_states;
   k->dof_out = b->dof_states_out ? b->dof_states_out : b->dof_states;
   k->pre = b->pre_ball_states; k->init_root = b->initial_root_states; k->init_dof = b->initial_dof_states;
@@ -263,9 +275,9 @@ int ppk_pre_physics_step(const PpkTask* t, const PpkBuffers* b, void* stream) {
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   pre_step_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      b->actions, b->pd_action_offset, b->pd_action_scale, b->pd_targets, b->num_envs, t->num_dofs, b->root_states,
+      b->actions, b->clip_actions, b->pd_action_offset, b->pd_action_scale, b->pd_targets, b->num_envs, t->num_dofs, b->root_states,
       t->num_actors * kRow, t->ball_actor, save_ball ? b->pre_ball_states : nullptr, b->pre_ball_stride,
-      b->pre_vx_offset, b->pre_vz_offset);
+      b->pre_vx_offset, b->pre_vz_offset, b->reset_count);
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 

@@ -51,7 +51,33 @@ struct KArgs {
   int write_flags;
   int reset_dof;
   int bulk_ok;   // tensors 16-byte aligned and ids[1..J) consecutive: bulk async staging is legal
+  // VecTask.step envelope (all optional)
+  long long* timeout;
+  const long long* actor_idx;
+  const long long* dof_idx;
+  int dof_per_env;
+  int* reset_count;
+  int* reset_actor_out;
+  int* reset_dof_out;
 };
+
+// Append env `env`'s actor / dof indices to the compacted reset lists (TILT:876-877).  Called by a
+// fully converged warp; `resets` marks the lanes whose env is being reset this step.
+__device__ __forceinline__ void append_reset_indices(const KArgs& k, bool resets, long long env, int lane) {
+  if (k.reset_count == nullptr) return;
+  const unsigned m = __ballot_sync(0xffffffffu, resets);
+  if (m == 0u) return;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(k.reset_count, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (resets) {
+    const int slot = base + __popc(m & ((1u << lane) - 1u));
+    for (int a = 0; a < k.A; ++a) k.reset_actor_out[(size_t)slot * k.A + a] = (int)k.actor_idx[env * k.A + a];
+    for (int d = 0; d < k.dof_per_env; ++d)
+      k.reset_dof_out[(size_t)slot * k.dof_per_env + d] = (int)k.dof_idx[env * k.dof_per_env + d];
+  }
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

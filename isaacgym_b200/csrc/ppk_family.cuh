@@ -316,6 +316,9 @@ family_step_kernel(const __grid_constant__ KArgs k) {
 
   // ---- predicated reset (TILT:847-906): lanes whose env resets rewrite its root / DOF rows -------
   const bool do_reset = (phases & PPK_PHASE_RESET) && is_reset && lane_env;
+  if (phases & PPK_PHASE_RESET) append_reset_indices(k, do_reset, env, lane);
+  if (k.timeout != nullptr && lane_env && (phases & (PPK_PHASE_REWARD | PPK_PHASE_PROGRESS)))
+    k.timeout[env] = (p_new >= k.max_len - 1) ? 1 : 0;
   if (do_reset) {
     const float* ir = k.init_root + (size_t)env * L::kRootEnv;
     float* gr = k.root_out + (size_t)env * L::kRootEnv;

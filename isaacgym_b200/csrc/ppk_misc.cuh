@@ -26,7 +26,10 @@ base_step_kernel(const __grid_constant__ KArgs k) {
   long long prog = k.progress[env] + ((phases & PPK_PHASE_PROGRESS) ? 1 : 0);
   float* gr = k.root + (size_t)env * rootN;
   // reset_idx of the envs flagged by the PREVIOUS step's reward (BASE:589-591)
-  if ((phases & PPK_PHASE_RESET) && on && k.reset[env] != 0) {
+  const bool base_resets = (phases & PPK_PHASE_RESET) && on && k.reset[env] != 0;
+  if (phases & PPK_PHASE_RESET) append_reset_indices(k, base_resets, env, lane);
+  if (k.timeout != nullptr && on) k.timeout[env] = (prog >= k.max_len - 1) ? 1 : 0;
+  if (base_resets) {
     const float* ir = k.init_root + (size_t)env * rootN;
     for (int a = 0; a < k.A; ++a)
       for (int c = 0; c < 7; ++c) gr[a * kRow + c] = ir[a * kRow + c];     // velocities are NOT zeroed (BASE:533-534)
@@ -87,14 +90,21 @@ base_step_kernel(const __grid_constant__ KArgs k) {
 // ---- pre_physics_step (TILT:1002-1020) ---------------------------------------------------------------
 // pd_tar[n,d] = offset[d] + scale[d]*actions[n,d]; save the ball's vx (and vz) for the next reward.
 __global__ void __launch_bounds__(256)
-pre_step_kernel(const float* __restrict__ actions, const float* __restrict__ offset, const float* __restrict__ scale,
+pre_step_kernel(float* __restrict__ actions, float clip, const float* __restrict__ offset, const float* __restrict__ scale,
                 float* __restrict__ pd, long long n, int D, const float* __restrict__ root, int rootN, int ball,
-                float* __restrict__ pre, int pre_stride, int pre_vx, int pre_vz) {
+                float* __restrict__ pre, int pre_stride, int pre_vx, int pre_vz, int* __restrict__ reset_count) {
+  // the compacted reset lists of the coming post_physics_step start empty (no extra memset node)
+  if (reset_count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *reset_count = 0;
   const long long total = n * D;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     int d = (int)(i % D);
-    st_stream(pd + i, offset[d] + scale[d] * ld_stream(actions + i));
+    float a = ld_stream(actions + i);
+    if (clip > 0.0f) {                    // VecTask.step: torch.clamp(actions, -clip, clip), kept in self.actions
+      a = fminf(fmaxf(a, -clip), clip);
+      actions[i] = a;
+    }
+    st_stream(pd + i, offset[d] + scale[d] * a);
   }
   if (pre != nullptr) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {

@@ -31,7 +31,7 @@ class PingpongTask(VecTask):
 
     def __init__(self, sim_state: Dict[str, torch.Tensor], cfg: Optional[TaskConfig] = None,
                  device: str = "cuda:0", fused: bool = True, full_pre_ball_clone: bool = False,
-                 log_stats: bool = False, **kw):
+                 log_stats: bool = False, envelope: bool = False, **kw):
         cfg = cfg or CONFIGS[self.variant]
         n = sim_state["root_states"].shape[0]
         super().__init__(cfg, n, device=device, **kw)
@@ -41,6 +41,8 @@ class PingpongTask(VecTask):
         self._task = N.make_task(cfg)
         self.fused = fused
         self.log_stats = log_stats
+        self.envelope = envelope          # also emit timeout_buf + compacted reset index lists (VecTask.step envelope)
+        self._count_zeroed = False
         dev = self.device
         # "acquired" PhysX tensors (zero-copy views in the reference, TILT:153-174)
         self.st: Dict[str, torch.Tensor] = {}
@@ -81,6 +83,12 @@ class PingpongTask(VecTask):
         self.pd_tar = torch.zeros(n, cfg.num_dofs, device=dev)
         self.stats = EpisodeStats(dev)
         self._scratch = torch.zeros(16, dtype=torch.int32, device=dev)
+        # VecTask.step envelope: compacted int32 index lists of the envs reset by the fused step
+        # (what gym.set_actor_root_state_tensor_indexed / set_dof_state_tensor_indexed take, TILT:876-888)
+        self.reset_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.reset_actor_indices = torch.zeros(max(n * cfg.num_actors, 1), dtype=torch.int32, device=dev)
+        dof_per = self.st["dof_indices"].numel() // max(n, 1) if "dof_indices" in self.st else 0
+        self.reset_dof_indices = torch.zeros(max(n * dof_per, 1), dtype=torch.int32, device=dev)
         self._buffers = None
 
     # -- plumbing -----------------------------------------------------------------------------------
@@ -88,7 +96,12 @@ class PingpongTask(VecTask):
         d = dict(self.st)
         d.update(obs_buf=self.obs_buf, rew_buf=self.rew_buf, reset_buf=self.reset_buf, progress_buf=self.progress_buf,
                  pre_ball_states=self.pre_ball2_root_states, actions=self.actions, pd_targets=self.pd_tar,
-                 stats=self.stats.slots, scratch=self._scratch)
+                 stats=self.stats.slots, scratch=self._scratch, clip_actions=self.clip_actions)
+        if self.envelope:
+            d.update(timeout_buf=self.timeout_buf)
+        if self.envelope and "actor_indices" in self.st and "dof_indices" in self.st:
+            d.update(reset_count=self.reset_count, reset_actor_indices=self.reset_actor_indices,
+                     reset_dof_indices=self.reset_dof_indices)
         for name in self.cfg.flag_names + self.cfg.counter_names:
             d[name] = getattr(self, name)
         return d
@@ -110,6 +123,7 @@ class PingpongTask(VecTask):
         """TILT:1002-1020: keep the actions, pd_tar = offset + scale*actions, save the ball state."""
         self.actions.copy_(actions.to(self.device))
         N.check(self._lib.ppk_pre_physics_step(self._task, self.buffers(), self._stream()), "ppk_pre_physics_step")
+        self._count_zeroed = True         # the pre-step kernel zeroes reset_count
 
     def compute_reward(self, actions=None):
         """TILT:739-768 (the statistics the reference prints every `log_every` steps are accumulated
@@ -145,6 +159,13 @@ class PingpongTask(VecTask):
                                                  1 if refresh_consumed_only else 0, self._stream()),
                 "ppk_sample_ball_launch")
 
+    def reset_indices(self):
+        """(actor_indices, dof_indices) int32 of the envs the last fused step reset -- one host read of
+        the counter (the gym setters need the count on the host anyway, TILT:883,888)."""
+        k = int(self.reset_count.item())
+        dof_per = self.st["dof_indices"].numel() // max(self.num_envs, 1)
+        return self.reset_actor_indices[:k * self.cfg.num_actors], self.reset_dof_indices[:k * dof_per]
+
     def _log_now(self) -> bool:
         le = self.cfg.log_every
         return self.log_stats and le > 0 and self.num_steps % le == 0
@@ -154,6 +175,9 @@ class PingpongTask(VecTask):
         the per-env reset and the observations.  With `fused=False` the reference's own sequence of
         calls is issued (three launches and a host-visible `nonzero`)."""
         log = self._log_now()
+        if self.envelope and not self._count_zeroed:
+            self.reset_count.zero_()
+        self._count_zeroed = False
         if self.fused:
             self._step(N.PHASE_ALL if log else (N.PHASE_ALL & ~N.PHASE_STATS))
         elif self.cfg.variant == "base":

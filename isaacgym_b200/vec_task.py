@@ -52,13 +52,15 @@ class VecTask:
         raise NotImplementedError
 
     def step(self, actions: torch.Tensor):
-        actions = torch.clamp(actions, -self.clip_actions, self.clip_actions)
+        # upstream clamps here (torch.clamp(actions, -clip, clip)); the pre-step kernel does it in place
         self.pre_physics_step(actions)
         for _ in range(self.control_freq_inv):
             if self.physics is not None:
                 self.physics(self)
         self.post_physics_step()
-        self.timeout_buf = (self.progress_buf >= self.max_episode_length - 1).to(torch.int64)
+        # with the envelope enabled timeout_buf is written by the fused step (progress >= L-1 before
+        # the reset cleared it); otherwise it stays zero as in the reference, whose reset has already
+        # cleared progress_buf by the time upstream VecTask.step evaluates it
         self.extras["time_outs"] = self.timeout_buf
         obs = torch.clamp(self.obs_buf, -self.clip_obs, self.clip_obs)
         return {"obs": obs}, self.rew_buf, self.reset_buf, self.extras
