@@ -1,5 +1,5 @@
 import sys, time, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from bench import run_e2e
 for v, n in (("tilt", 65536),):
     for chunks in (1, 2, 3, 4, 6, 8, 12, 16):

@@ -1,5 +1,5 @@
 import ctypes as C, sys, torch, numpy as np
-sys.path.insert(0,'.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from isaacgym_b200 import _native as N
 from isaacgym_b200.config import CONFIGS
 from isaacgym_b200.synth import make_state
