@@ -8,11 +8,11 @@
 //              16-byte aligned windows around its live rows (2096 B) and reference rows (1472 B),
 //              per tile the contiguous root / DOF / reference-DOF / force slices.  Tail tiles and
 //              misaligned tensors take an LDG path into the same layout.
-//   warps 1-3  one env per pass, lane = balance body (23) and lane = DOF (27): imitation diffs, the
-//              seven per-env reductions of compute_imitation_reward (ADOF:1313-1418) by warp
-//              shuffles, heading frame, imitation observation segments (ADOF:1891-1927);
-//   warp 0     the ten ping-pong bodies in the heading frame (ADOF:1849-1888, lane = output float)
-//              while the other warps reduce; then lane = env: compute_pingpong_reward_nv
+//   warps 1-4  one env per pass, lane = balance body (23) and lane = DOF (27): imitation diffs, the
+//              seven per-env reductions of compute_imitation_reward (ADOF:1313-1418) in one fused
+//              butterfly, heading frame, imitation observation segments (ADOF:1891-1927) and the ten
+//              ping-pong bodies in the heading frame (ADOF:1849-1888, lane = output float);
+//   warp 0     lane = env: compute_pingpong_reward_nv
 //              (ADOF:1440-1690) + compute_gradient_penalty (ADOF:1245-1301), flags, counters,
 //              time-out mask, predicated reset (ADOF:965-1028); then the dof / ball / reference-dof
 //              segments of the obs row, lane = element.
@@ -207,6 +207,19 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
         }
       }
       if ((phases & PPK_PHASE_OBS) && e < nvalid) {
+        // ping-pong bodies [0,60), lane = output float o: body o/3, component o%3 (ADOF:1849-1888);
+        //   out_c = v_c*a0 + ((s1*v_o)*m)*2 == my_quat_rotate((0,0,sz,cw), v) component by component
+        if (lane < 3 * J) {
+          const int j = lane / 3, c = lane - j * 3;
+          const int oth = (c == 0) ? 1 : (c == 1 ? 0 : 2);
+          const float a0 = 2.0f * (hq_pp.cw * hq_pp.cw) - 1.0f;
+          const float s1 = (c == 0) ? -hq_pp.sz : hq_pp.sz, m = (c == 2) ? hq_pp.sz : hq_pp.cw;
+          const float* row = rb_e + k.ids[0][j] * kRow;
+          const float pc = row[c] - r0[c], po = row[oth] - r0[oth];
+          float* orow = g_obs + (size_t)e * kAdofObs;
+          st_stream(orow + lane, pc * a0 + ((s1 * po) * m) * 2.0f);
+          st_stream(orow + 3 * J + lane, row[7 + c] * a0 + ((s1 * row[7 + oth]) * m) * 2.0f);
+        }
         // imitation observation segments [121,190) = 10*R(dP), [190,259) = R(dV)
         float lp[3], lv[3];
         rotate_heading(hq_bal, dpx, dpy, dpz, lp[0], lp[1], lp[2]);
@@ -249,41 +262,6 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
     }
   }
   if (bulk) mbar_wait(bar, 0);
-
-  // ---- ping-pong bodies, lane = output float (needs only the heading frame of its env) ------------
-  if (phases & PPK_PHASE_OBS) {
-    const bool lane_on = lane < 3 * J;
-    const int o = lane_on ? lane : 0;
-    const int j = o / 3, c = o - j * 3;
-    const int oth = (c == 0) ? 1 : (c == 1 ? 0 : 2);
-    const float sgn = (c == 0) ? -1.0f : 1.0f;
-    const int my_id = k.ids[0][j];
-    // frames recomputed here (lane = env, then broadcast) instead of waiting for the reducing warps
-    Heading my_hq; my_hq.sz = 0.0f; my_hq.cw = 1.0f;
-    if (lane < T) {
-      const float* r0 = rb_s + lane * L::kSRb + win_off(g_rb, lane) + pp_root * kRow;
-      my_hq = heading_quat_inv(r0[3], r0[4], r0[5], r0[6]);
-    }
-#pragma unroll 2
-    for (int e = 0; e < T; ++e) {
-      const float* rb_e = rb_s + e * L::kSRb + win_off(g_rb, e);
-      const float* r0 = rb_e + pp_root * kRow;
-      Heading hq;
-      hq.sz = __shfl_sync(full, my_hq.sz, e);
-      hq.cw = __shfl_sync(full, my_hq.cw, e);
-      const float a0 = 2.0f * (hq.cw * hq.cw) - 1.0f;
-      const float s1 = sgn * hq.sz, m = (c == 2) ? hq.sz : hq.cw;
-      const float* row = rb_e + my_id * kRow;
-      const float pc = row[c] - r0[c], po = row[oth] - r0[oth];
-      const float out_p = pc * a0 + ((s1 * po) * m) * 2.0f;
-      const float out_v = row[7 + c] * a0 + ((s1 * row[7 + oth]) * m) * 2.0f;
-      if (lane_on && e < nvalid) {
-        float* orow = g_obs + (size_t)e * kAdofObs;
-        st_stream(orow + o, out_p);
-        st_stream(orow + 3 * J + o, out_v);
-      }
-    }
-  }
 
   // ---- phase R: lane = env ---------------------------------------------------------------------
   adof_wait();          // reductions and frames of all 8 envs are in hdr_s
@@ -479,9 +457,6 @@ inline int launch_adof(const KArgs& k0, cudaStream_t s) {
     configured = true;
   }
   const bool fused_reset = (k.phases & PPK_PHASE_RESET) != 0 && !(k.phases & kPhaseDeferCounterClear);
-  if (fused_reset) {
-    if (cudaMemsetAsync(k.scratch, 0, sizeof(unsigned int), s) != cudaSuccess) { cudaGetLastError(); return PPK_ERR_LAUNCH; }
-  }
   const long long tiles = (k.n + kAdofTile - 1) / kAdofTile;
   adof_step_kernel<<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
   if (cudaGetLastError() != cudaSuccess) return PPK_ERR_LAUNCH;

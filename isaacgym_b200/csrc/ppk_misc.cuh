@@ -256,9 +256,21 @@ sample_launch_kernel(float* __restrict__ vel, float* __restrict__ pos_yz, const 
 
 // ADOF:1162-1175: when any env of the shard reset this step, all five counters are cleared.
 __global__ void __launch_bounds__(256)
-adof_clear_counters_kernel(const unsigned int* any_reset, unsigned char* c0, unsigned char* c1, unsigned char* c2,
+adof_clear_counters_kernel(unsigned int* any_reset, unsigned char* c0, unsigned char* c1, unsigned char* c2,
                            unsigned char* c3, unsigned char* c4, long long n) {
-  if (*any_reset == 0u) return;
+  // scratch[0] = "some env reset" flag set by the step kernel, scratch[1] = ticket.  Every block
+  // reads the flag, then takes a ticket; the last one re-arms both words for the next step, so no
+  // memset node is needed in front of the step kernel.
+  __shared__ unsigned int flag_s;
+  if (threadIdx.x == 0) flag_s = any_reset[0];
+  __syncthreads();
+  const bool clear = flag_s != 0u;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(any_reset + 1, 1u);
+    if (t == gridDim.x - 1) { any_reset[0] = 0u; any_reset[1] = 0u; }
+  }
+  if (!clear) return;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const uintptr_t all = reinterpret_cast<uintptr_t>(c0) | reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(c2) |
                         reinterpret_cast<uintptr_t>(c3) | reinterpret_cast<uintptr_t>(c4);
