@@ -190,7 +190,7 @@ def time_steps(tasks, steps, warmup, with_pre, log_every, world, dist):
         t = torch.tensor([sec], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
-    per_step = 1 + (1 if with_pre else 0) + (2 if tasks[0].cfg.variant == "adof" else 0)
+    per_step = 1 + (1 if with_pre else 0) + (1 if tasks[0].cfg.variant == "adof" else 0)   # ADOF: + counter-clear kernel
     return sec, steps * per_step
 
 
