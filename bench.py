@@ -39,12 +39,13 @@ WORKLOADS = {
     "a4": ("a4", 65536, "configs[3]: humanoid_pingpong_4_actor_tilt shard", False),
     "adof": ("adof", 32768, "configs[3]: humanoid_pingpong_3_actor_all_dof shard", False),
     "align": ("align", 131072, "configs[4]: humanoid_pingpong_alignment full task step, 131072 envs/GPU", True),
+    "align2": ("align2", 65536, "humanoid_pingpong_alignment reward definition #2 (two humanoids, last_hitter), 65536 envs/GPU", False),
     "nes": ("nes", 65536, "humanoid_pingpong_3_actor_tilt_no_earlystop 65536 envs/GPU", False),
     "tilt_1m": ("tilt", 1048576, "humanoid_pingpong_3_actor_tilt 1M envs/GPU (launch overhead amortised)", False),
 }
 # algorithmic bytes per env-step (A_core + 8 for the progress write-back; the
 # full ALIGN step adds the pre-step 72 B; reset traffic is ~3 B/env-step and not counted)
-ALGO_BYTES = {"base": 212 + 8, "a3": 708 + 8, "tilt": 718 + 8, "nes": 716 + 8, "align": 718 + 8, "a4": 1504 + 8,
+ALGO_BYTES = {"base": 212 + 8, "a3": 708 + 8, "tilt": 718 + 8, "nes": 716 + 8, "align": 718 + 8, "a4": 1504 + 8, "align2": 1519 + 8,
               "adof": 3198 + 8}
 PRE_STEP_BYTES = {"align": 72}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the ncu --set full captures under profiles/

@@ -57,7 +57,9 @@ typedef enum PpkVariant {
   PPK_NES = 3,    /* humanoid_pingpong_3_actor_tilt_no_earlystop.py                        */
   PPK_ALIGN = 4,  /* humanoid_pingpong_alignment.py (reward definition #1, ALIGN:1097)     */
   PPK_A4 = 5,     /* humanoid_pingpong_4_actor_tilt.py (two humanoids)                     */
-  PPK_ADOF = 6    /* humanoid_pingpong_3_actor_all_dof.py (27 DOF, imitation terms)        */
+  PPK_ADOF = 6,   /* humanoid_pingpong_3_actor_all_dof.py (27 DOF, imitation terms)        */
+  PPK_ALIGN2 = 7  /* humanoid_pingpong_alignment.py reward definition #2 (ALIGN:1233-1351):
+                     two humanoids on the A4 tensor layout, `last_hitter` state (8(f) rank 3) */
 } PpkVariant;
 
 /* Phases of post_physics_step (TILT:1022-1052); OR them together. */
@@ -143,7 +145,7 @@ typedef struct PpkBuffers {
    *  TILT  0 condition_calculated 1 reward_calculated 2 no_bounce_before_half_mask (TILT:241-243)
    *  A4    0..2 humanoid 1 as TILT, 3..5 humanoid 2
    *  NES   0 paddle_condition_calculated 1 missed_ball_calculated (NES:759-760)
-   *  ALIGN 0 reward_calculated (ALIGN:239)
+   *  ALIGN, ALIGN2 0 reward_calculated (ALIGN:239)
    *  ADOF  0 paddle_condition_calculated 1 hit_table_calculated 2 die_penalty_calculated
    *        3 humanoid_die_calculated 4 closer_to_paddle_count 5 hit_paddle_count
    *        6 cross_net_count 7 hit_table_count 8 fall_down_count (ADOF:279-293)             */
@@ -182,6 +184,9 @@ typedef struct PpkBuffers {
   int32_t* reset_count;                 /* [1] device                                         */
   int32_t* reset_actor_indices;         /* [N*A] capacity                                     */
   int32_t* reset_dof_indices;           /* [N*dof_indices_per_env] capacity                   */
+  /* ALIGN2 only: who hit the ball last, 1 or 2 (ALIGN:1253, returned by the reward ALIGN:1349-1351;
+   * read + written; a reset puts it back to its initial value 2) */
+  int64_t* last_hitter;
 } PpkBuffers;
 
 PPK_API int ppk_abi_version(void);

@@ -52,6 +52,7 @@ class PpkBuffers(C.Structure):
         ("clip_actions", C.c_float), ("dof_indices_per_env", C.c_int32), ("timeout_buf", C.c_void_p),
         ("actor_indices", C.c_void_p), ("dof_indices", C.c_void_p), ("reset_count", C.c_void_p),
         ("reset_actor_indices", C.c_void_p), ("reset_dof_indices", C.c_void_p),
+        ("last_hitter", C.c_void_p),
     ]
 
 
@@ -140,7 +141,7 @@ def make_task(cfg: TaskConfig) -> PpkTask:
     t.is_train = 1 if cfg.is_train else 0
     t.reset_dof = 1 if cfg.reset_dof else 0
     # eager reward functions mutate the caller's flags; the TorchScript ones (ALIGN, A4) do not (D16)
-    t.write_flags = 0 if cfg.variant in ("align", "a4") else 1
+    t.write_flags = 0 if cfg.variant in ("align", "a4", "align2") else 1
     return t
 
 
@@ -204,6 +205,7 @@ def make_buffers(cfg: TaskConfig, st: dict, host: bool = False) -> PpkBuffers:
     b.pd_targets = get("pd_targets", f32, (n, D))
     b.stats = _ptr(st.get("stats"), torch.float64, "stats", host)
     b.scratch = _ptr(st.get("scratch"), torch.int32, "scratch", host)
+    b.last_hitter = _ptr(st.get("last_hitter"), i64, "last_hitter", host)
     # optional VecTask.step envelope outputs
     b.clip_actions = float(st.get("clip_actions", 0.0) or 0.0)
     b.timeout_buf = _ptr(st.get("timeout_buf"), i64, "timeout_buf", host)

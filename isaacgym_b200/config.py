@@ -16,7 +16,7 @@ BODY_IDS_PINGPONG: Tuple[int, ...] = (0, 31, 32, 33, 34, 35, 36, 37, 38, 39)
 # cfg/task/HumanoidPingpongTiltNESSparse27DOFG1.yaml:57
 BODY_IDS_BALANCE: Tuple[int, ...] = (0, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 21, 22, 23, 24, 25, 26, 27)
 
-VARIANT_IDS = {"base": 0, "a3": 1, "tilt": 2, "nes": 3, "align": 4, "a4": 5, "adof": 6}
+VARIANT_IDS = {"base": 0, "a3": 1, "tilt": 2, "nes": 3, "align": 4, "a4": 5, "adof": 6, "align2": 7}
 
 
 @dataclass(frozen=True)
@@ -50,6 +50,7 @@ class TaskConfig:
     flag_reset_values: Tuple[bool, ...] = ()
     counter_names: Tuple[str, ...] = ()
     reset_dof: bool = True             # NES leaves the DOF state alone (NES:871-918)
+    state_names: Tuple[str, ...] = ()  # extra per-env int64 state tensors (ALIGN def #2: last_hitter)
 
     @property
     def variant_id(self) -> int:
@@ -89,6 +90,14 @@ CONFIGS = {
                       body_ids_2=tuple(i + 40 for i in BODY_IDS_PINGPONG),
                       flag_names=_TILT_FLAGS + tuple(n + "_2" for n in _TILT_FLAGS),
                       flag_reset_values=(False, False, True, False, False, True)),
+    # ALIGN's second reward definition (ALIGN:1233-1351): two humanoids on the
+    # 4-actor layout of A4, one shared `reward_calculated` flag and an int64 `last_hitter` state
+    # ("initialised to 2", ALIGN:1253).  The reference never ran it (defect D7); constants as ALIGN.
+    "align2": _TILT.with_(variant="align2", num_actors=4, num_bodies=82, num_dofs=14, num_obs=94, obs_rows=2,
+                          humanoid_actor=(0, 1), ball_actor=3, paddle_body=(39, 79),
+                          body_ids_2=tuple(i + 40 for i in BODY_IDS_PINGPONG),
+                          flag_names=("reward_calculated",), flag_reset_values=(False,),
+                          state_names=("last_hitter",)),
     # cfg/task/HumanoidPingpongTiltNESSparse27DOFG1.yaml:10-30,56-57
     "adof": TaskConfig(variant="adof", num_actors=3, num_bodies=42, num_dofs=27, num_obs=313,
                        balance_ids=BODY_IDS_BALANCE, max_episode_length=160, alpha=3000.0,

@@ -16,13 +16,14 @@ namespace {
 int fill_args(const PpkTask* t, const PpkBuffers* b, uint32_t phases, KArgs* k) {
   if (t == nullptr || b == nullptr) return PPK_ERR_NULL;
   if (t->struct_size != sizeof(PpkTask) || b->struct_size != sizeof(PpkBuffers)) return PPK_ERR_ABI;
-  if (t->variant < PPK_BASE || t->variant > PPK_ADOF) return PPK_ERR_VARIANT;
+  if (t->variant < PPK_BASE || t->variant > PPK_ALIGN2) return PPK_ERR_VARIANT;
   if (b->num_envs < 0 || t->num_actors <= 0 || t->num_bodies <= 0 || t->num_dofs <= 0) return PPK_ERR_SHAPE;
   if (t->num_body_ids < 0 || t->num_body_ids > PPK_MAX_BODY_IDS || t->num_balance_ids < 0 ||
       t->num_balance_ids > PPK_MAX_BODY_IDS)
     return PPK_ERR_SHAPE;
   memset(k, 0, sizeof(*k));
   k->rb = b->rigid_body_states; k->root = b->root_states; k->dof = b->dof_states; k->force = b->dof_forces;
+  k->last_hitter = reinterpret_cast<long long*>(b->last_hitter);
   k->timeout = reinterpret_cast<long long*>(b->timeout_buf);
   if (b->reset_count != nullptr) {
     if (!b->actor_indices || !b->reset_actor_indices || b->dof_indices_per_env < 0 ||
@@ -53,7 +54,7 @@ int fill_args(const PpkTask* t, const PpkBuffers* b, uint32_t phases, KArgs* k) 
     k->paddle_j[h] = -1;
     for (int j = 0; j < t->num_body_ids; ++j) {
       int id = t->body_ids[h][j];
-      if (h == 0 || t->variant == PPK_A4) {
+      if (h == 0 || t->variant == PPK_A4 || t->variant == PPK_ALIGN2) {
         if (id < 0 || id >= t->num_bodies) return PPK_ERR_SHAPE;
       }
       k->ids[h][j] = id;
@@ -81,7 +82,7 @@ int fill_args(const PpkTask* t, const PpkBuffers* b, uint32_t phases, KArgs* k) 
   if (bulk) {
     const void* al[] = {b->rigid_body_states, b->root_states, b->dof_states, b->dof_forces};
     for (const void* p : al) bulk = bulk && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
-    const int nh = (t->variant == PPK_A4) ? 2 : 1;
+    const int nh = (t->variant == PPK_A4 || t->variant == PPK_ALIGN2) ? 2 : 1;
     for (int h = 0; h < nh && bulk; ++h) {
       for (int j = 2; j < t->num_body_ids; ++j) bulk = bulk && (t->body_ids[h][j] == t->body_ids[h][1] + j - 1);
       bulk = bulk && (t->body_ids[h][0] + 1 < t->num_bodies) && (t->body_ids[h][t->num_body_ids - 1] + 1 < t->num_bodies);
@@ -99,6 +100,7 @@ int num_flags_of(int variant) {
     case PPK_A4: return 6;
     case PPK_NES: return 2;
     case PPK_ALIGN: return 1;
+    case PPK_ALIGN2: return 1;
     case PPK_ADOF: return 9;
     default: return 0;
   }
@@ -119,6 +121,7 @@ int check_step_pointers(const PpkTask* t, const PpkBuffers* b, uint32_t phases) 
     if (!b->initial_body_states || !b->initial_dof_states) return PPK_ERR_NULL;
     if (rst && (!b->reset_ball_pos_yz || !b->scratch)) return PPK_ERR_NULL;
   }
+  if (v == PPK_ALIGN2 && (rew || rst) && !b->last_hitter) return PPK_ERR_NULL;
   if ((phases & PPK_PHASE_STATS) && !b->stats) return PPK_ERR_NULL;
   if (rew || rst)
     for (int i = 0; i < num_flags_of(v); ++i)
@@ -132,7 +135,7 @@ int check_step_pointers(const PpkTask* t, const PpkBuffers* b, uint32_t phases) 
   if (b->stats && misaligned(b->stats, 8)) return PPK_ERR_ALIGN;
   if (rew && v != PPK_BASE && (b->pre_ball_stride <= 0 || b->pre_vx_offset < 0 || b->pre_vx_offset >= b->pre_ball_stride))
     return PPK_ERR_SHAPE;
-  if (rew && v == PPK_ALIGN && (b->pre_vz_offset < 0 || b->pre_vz_offset >= b->pre_ball_stride)) return PPK_ERR_SHAPE;
+  if (rew && (v == PPK_ALIGN || v == PPK_ALIGN2) && (b->pre_vz_offset < 0 || b->pre_vz_offset >= b->pre_ball_stride)) return PPK_ERR_SHAPE;
   return PPK_OK;
 }
 
@@ -203,6 +206,9 @@ int ppk_post_physics_step(const PpkTask* t, const PpkBuffers* b, uint32_t phases
     case PPK_A4:
       if (t->num_actors != 4 || t->num_dofs != 14 || t->num_body_ids != 10) return PPK_ERR_SHAPE;
       return launch_family<PPK_A4, 2, 10, 14, 4, 8, 1>(k, s);
+    case PPK_ALIGN2:
+      if (t->num_actors != 4 || t->num_dofs != 14 || t->num_body_ids != 10) return PPK_ERR_SHAPE;
+      return launch_family<PPK_ALIGN2, 2, 10, 14, 4, 8, 1>(k, s);
     case PPK_ADOF:
       if (t->num_actors != 3 || t->num_dofs != 27 || t->num_body_ids != 10 || t->num_balance_ids != 23) return PPK_ERR_SHAPE;
       return launch_adof(k, s);
@@ -245,6 +251,8 @@ int ppk_reset_idx(const PpkTask* t, const PpkBuffers* b, const int64_t* env_ids,
   r.dof_per_env = dof_indices_out ? dof_indices_per_env : 0;
   r.actor_out = actor_indices_out; r.dof_out = dof_indices_out;
   r.variant = t->variant;
+  r.last_hitter = reinterpret_cast<long long*>(b->last_hitter);
+  if (t->variant == PPK_ALIGN2 && !b->last_hitter) return PPK_ERR_NULL;
   // flags written by _reset_idx: TILT:902-905, NES:913-917, ALIGN:897, A4:908-911, ADOF:1023-1026
   // (ADOF resets only its four *_calculated flags; the five counters are cleared elsewhere)
   int nf = num_flags_of(t->variant);
@@ -285,7 +293,7 @@ int ppk_sample_ball_launch(const PpkTask* t, const PpkBuffers* b, uint64_t seed,
                            int32_t refresh_consumed_only, void* stream) {
   if (t == nullptr || b == nullptr) return PPK_ERR_NULL;
   if (t->struct_size != sizeof(PpkTask) || b->struct_size != sizeof(PpkBuffers)) return PPK_ERR_ABI;
-  if (t->variant <= PPK_BASE || t->variant > PPK_ADOF) return PPK_ERR_VARIANT;
+  if (t->variant <= PPK_BASE || t->variant > PPK_ALIGN2) return PPK_ERR_VARIANT;
   if (b->num_envs < 0 || env_offset < 0) return PPK_ERR_SHAPE;
   if (b->num_envs == 0) return PPK_OK;
   if (!b->reset_ball_vel || (t->variant == PPK_ADOF && !b->reset_ball_pos_yz)) return PPK_ERR_NULL;

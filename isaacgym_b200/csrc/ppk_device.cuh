@@ -51,6 +51,7 @@ struct KArgs {
   int write_flags;
   int reset_dof;
   int bulk_ok;   // tensors 16-byte aligned and ids[1..J) consecutive: bulk async staging is legal
+  long long* last_hitter;   // ALIGN2
   // VecTask.step envelope (all optional)
   long long* timeout;
   const long long* actor_idx;
@@ -272,6 +273,33 @@ __device__ __forceinline__ float reward_align(const Scene& s, const KArgs& k, bo
   if (s.bx < s.hx - 0.05f) r = r + k.penalty;
   die = s.bz < 0.1f;
   return r;
+}
+
+// ALIGN:1233-1351 (two humanoids; returns both rewards, updates last_hitter).  `rc` is the caller's
+// reward_calculated flag; the function is TorchScript, so its `|=` updates stay local (D16).
+__device__ __forceinline__ void reward_align2(const Scene& s1, const Scene& s2, const KArgs& k, bool rc, long long& last_hitter,
+                                              float& r1, float& r2, bool& die) {
+  const float d1 = dist3(s1), d2 = dist3(s2);
+  const float pos1 = 1.0f / (1.0f + 1.5f * d1 * d1), pos2 = 1.0f / (1.0f + 1.5f * d2 * d2);
+  const bool c1 = (s1.pre_vx < 0.0f) && (s1.vx > 0.0f);
+  const bool c2 = (s1.pre_vx > 0.0f) && (s1.vx < 0.0f);
+  const float vel1 = c1 ? k.alpha * fabsf(s1.vx) : 0.0f;
+  const float vel2 = c2 ? k.alpha * fabsf(s1.vx) : 0.0f;
+  const bool range1 = (s1.bx > 2.2f) && (s1.bx < 3.1f);
+  const bool range2 = (s1.bx < 1.3f) && (s1.bx > 0.4f);
+  const bool bounce_up = (s1.pre_vz < 0.0f) && (s1.vz > 0.0f);
+  float hit1 = (range1 && bounce_up && last_hitter == 1 && !rc) ? k.hit_table : 0.0f;
+  float hit2 = (range2 && bounce_up && last_hitter == 2 && !rc) ? k.hit_table : 0.0f;
+  rc = rc || (range1 && bounce_up) || (range2 && bounce_up);
+  if ((s1.bx >= 3.1f) && last_hitter == 1 && !rc) hit1 = k.not_hit;
+  if ((s1.bx <= -3.1f) && last_hitter == 2 && !rc) hit2 = k.not_hit;
+  r1 = ((pos1 + s1.power_reward) + vel1) + hit1;
+  r2 = ((pos2 + s1.power_reward) + vel2) + hit2;
+  if (s1.bx < s1.hx - 0.05f) r1 = r1 + k.penalty;
+  if (s1.bx > s2.hx + 0.05f) r2 = r2 + k.penalty;
+  die = s1.bz < 0.1f;
+  if (c1) last_hitter = 1;
+  if (c2) last_hitter = 2;
 }
 
 }  // namespace ppk

@@ -208,7 +208,8 @@ family_step_kernel(const __grid_constant__ KArgs k) {
   const long long env = env0 + (lane_env ? lane : 0);
   long long prog = 0, reset_prev = 0;
   float pre_vx = 0.0f, pre_vz = 0.0f;
-  constexpr int NF = (V == PPK_TILT) ? 3 : (V == PPK_A4) ? 6 : (V == PPK_NES) ? 2 : (V == PPK_ALIGN) ? 1 : 0;
+  constexpr int NF = (V == PPK_TILT) ? 3 : (V == PPK_A4) ? 6 : (V == PPK_NES) ? 2 : (V == PPK_ALIGN || V == PPK_ALIGN2) ? 1 : 0;
+  long long last_hitter = 2;
   bool flag[NF > 0 ? NF : 1];
   // per-env scalars come straight from global and overlap the bulk copies
   const float* g_root = k.root + (size_t)env * L::kRootEnv;
@@ -224,7 +225,8 @@ family_step_kernel(const __grid_constant__ KArgs k) {
     if (phases & PPK_PHASE_REWARD) {
       const float* p = k.pre + (size_t)env * k.pre_stride;
       pre_vx = ld_stream(p + k.pre_vx);
-      if (V == PPK_ALIGN) pre_vz = ld_stream(p + k.pre_vz);
+      if (V == PPK_ALIGN || V == PPK_ALIGN2) pre_vz = ld_stream(p + k.pre_vz);
+      if (V == PPK_ALIGN2) last_hitter = k.last_hitter[env];
 #pragma unroll
       for (int i = 0; i < NF; ++i) flag[i] = k.flags[i][env] != 0;
     }
@@ -265,9 +267,10 @@ family_step_kernel(const __grid_constant__ KArgs k) {
 #pragma unroll
     for (int d = 0; d < D; ++d) power += fabsf(force_s[le * D + d] * dofv[2 * d + 1]);
     bool die = false;
+    Scene sc[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      Scene s;
+      Scene& s = sc[h];
       s.bx = bx; s.by = by; s.bz = bz; s.vx = bvx; s.vz = bvz;
       s.pre_vx = pre_vx; s.pre_vz = pre_vz;
       const int pj = k.paddle_j[h];
@@ -283,6 +286,10 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       s.hx = hx[h];
       s.power_reward = (-k.power_coef) * power;
       s.progress = p_new;
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const Scene& s = sc[h];
       bool d = false;
       if (V == PPK_A3) rew[h] = reward_a3(s, k, d);
       if (V == PPK_TILT) rew[h] = reward_tilt<false>(s, k, flag[0], flag[1], flag[2], d);
@@ -294,6 +301,7 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       }
       die = die || d;
     }
+    if (V == PPK_ALIGN2) reward_align2(sc[0], sc[H - 1], k, flag[0], last_hitter, rew[0], rew[H - 1], die);
     is_reset = (p_new >= k.max_len - 1) || die;
     if (lane_env) {
 #pragma unroll
@@ -345,6 +353,10 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       }
     }
     p_new = 0;
+  }
+  if (V == PPK_ALIGN2 && lane_env && (phases & (PPK_PHASE_REWARD | PPK_PHASE_RESET))) {
+    if (do_reset) k.last_hitter[env] = 2;                       // a fresh rally starts with its initial value (ALIGN:1253)
+    else if (phases & PPK_PHASE_REWARD) k.last_hitter[env] = last_hitter;
   }
   if (lane_env) {
     if (phases & (PPK_PHASE_PROGRESS | PPK_PHASE_RESET)) k.progress[env] = p_new;

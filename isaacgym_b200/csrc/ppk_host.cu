@@ -43,7 +43,7 @@ struct PpkHostSession {
   float *rb = nullptr, *root = nullptr, *dof = nullptr, *force = nullptr, *pre = nullptr;
   float *init_root = nullptr, *init_dof = nullptr, *init_rb = nullptr, *reset_vel = nullptr, *reset_yz = nullptr;
   float *obs = nullptr, *rew = nullptr;
-  int64_t *reset = nullptr, *progress = nullptr;
+  int64_t *reset = nullptr, *progress = nullptr, *last_hitter = nullptr;
   uint8_t* flags[PPK_MAX_FLAGS] = {};
   double* stats = nullptr;
   uint32_t* scratch = nullptr;
@@ -77,6 +77,7 @@ int flags_of(int variant) {
     case PPK_A4: return 6;
     case PPK_NES: return 2;
     case PPK_ALIGN: return 1;
+    case PPK_ALIGN2: return 1;
     case PPK_ADOF: return 9;
     default: return 0;
   }
@@ -130,8 +131,9 @@ int enqueue_step(PpkHostSession* s, const PpkBuffers* hb, uint32_t phases) {
   const PpkTask& t = s->host_task;
   const int v = t.variant, A = t.num_actors, D = t.num_dofs, B = t.num_bodies, Bd = s->dev_bodies;
   const bool rew = phases & PPK_PHASE_REWARD, rst = phases & PPK_PHASE_RESET, obs = phases & PPK_PHASE_OBS;
-  const int obs_w = (v == PPK_BASE) ? 24 : (v == PPK_ADOF) ? 313 : (v == PPK_A4) ? 2 * 94 : 80;
-  const int rew_w = (v == PPK_A4) ? 2 : 1;
+  const bool two = (v == PPK_A4 || v == PPK_ALIGN2);
+  const int obs_w = (v == PPK_BASE) ? 24 : (v == PPK_ADOF) ? 313 : two ? 2 * 94 : 80;
+  const int rew_w = two ? 2 : 1;
   const int pre_stride = hb->pre_ball_stride > 0 ? hb->pre_ball_stride : 2;
   s->h2d_bytes = 0;
   s->d2h_bytes = 0;
@@ -174,6 +176,10 @@ int enqueue_step(PpkHostSession* s, const PpkBuffers* hb, uint32_t phases) {
         s->h2d_bytes += m;
       }
     if (zc && rew && v != PPK_BASE) s->h2d_bytes += sizeof(float) * m * 2;   // saved ball velocity read in place
+    if (v == PPK_ALIGN2 && rew) {
+      if (!zc) CU(cudaMemcpyAsync(s->last_hitter + lo, hb->last_hitter + lo, sizeof(int64_t) * m, cudaMemcpyHostToDevice, st));
+      s->h2d_bytes += sizeof(int64_t) * m;
+    }
 
     // ---- the fused step on the chunk
     PpkBuffers db;
@@ -198,7 +204,9 @@ int enqueue_step(PpkHostSession* s, const PpkBuffers* hb, uint32_t phases) {
     for (int i = 0; i < s->num_flags; ++i) db.flags[i] = s->flags[i] + lo;
     db.stats = s->stats;
     db.scratch = s->scratch;
+    db.last_hitter = s->last_hitter ? s->last_hitter + lo : nullptr;
     if (zc) {
+      if (hb->last_hitter) db.last_hitter = hb->last_hitter + lo;
       if (hb->pre_ball_states) db.pre_ball_states = hb->pre_ball_states + (size_t)lo * pre_stride;
       db.rew_buf = hb->rew_buf ? hb->rew_buf + (size_t)lo * rew_w : db.rew_buf;
       db.reset_buf = hb->reset_buf + lo;
@@ -229,6 +237,10 @@ int enqueue_step(PpkHostSession* s, const PpkBuffers* hb, uint32_t phases) {
       CU(cudaMemcpyAsync(hb->root_states + (size_t)lo * A * kRow, s->root + (size_t)lo * A * kRow, sizeof(float) * m * A * kRow, cudaMemcpyDeviceToHost, st));
       s->d2h_bytes += sizeof(float) * m * A * kRow;
       if (t.reset_dof) { CU(cudaMemcpyAsync(hb->dof_states + (size_t)lo * D * 2, s->dof + (size_t)lo * D * 2, sizeof(float) * m * D * 2, cudaMemcpyDeviceToHost, st)); s->d2h_bytes += sizeof(float) * m * D * 2; }
+    }
+    if (v == PPK_ALIGN2 && (rew || rst)) {
+      if (!zc) CU(cudaMemcpyAsync(hb->last_hitter + lo, s->last_hitter + lo, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, st));
+      s->d2h_bytes += sizeof(int64_t) * m;
     }
     if (rew || rst) {
       const int nf = adof_deferred ? 4 : s->num_flags;
@@ -276,7 +288,7 @@ int ppk_host_session_destroy(PpkHostSession* s) {
   for (cudaStream_t st : s->streams)
     if (st) cudaStreamDestroy(st);
   void* ptrs[] = {s->rb, s->root, s->dof, s->force, s->pre, s->init_root, s->init_dof, s->init_rb, s->reset_vel,
-                  s->reset_yz, s->obs, s->rew, s->reset, s->progress, s->stats, s->scratch};
+                  s->reset_yz, s->obs, s->rew, s->reset, s->progress, s->last_hitter, s->stats, s->scratch};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (uint8_t* f : s->flags)
@@ -288,7 +300,7 @@ int ppk_host_session_destroy(PpkHostSession* s) {
 int ppk_host_session_create(const PpkTask* task, int64_t max_envs, int32_t num_chunks, PpkHostSession** out) {
   if (!task || !out) return PPK_ERR_NULL;
   if (task->struct_size != sizeof(PpkTask)) return PPK_ERR_ABI;
-  if (max_envs <= 0 || num_chunks <= 0 || task->variant < PPK_BASE || task->variant > PPK_ADOF) return PPK_ERR_SHAPE;
+  if (max_envs <= 0 || num_chunks <= 0 || task->variant < PPK_BASE || task->variant > PPK_ALIGN2) return PPK_ERR_SHAPE;
   PpkHostSession* s = new (std::nothrow) PpkHostSession();
   if (!s) return PPK_ERR_CUDA;
   memset(&s->key, 0, sizeof(s->key));
@@ -311,10 +323,10 @@ int ppk_host_session_create(const PpkTask* task, int64_t max_envs, int32_t num_c
     next = 2;
   } else {
     add_ids(s->runs, task->body_ids[0], task->num_body_ids, d.body_ids[0], next);
-    if (task->variant == PPK_A4) add_ids(s->runs, task->body_ids[1], task->num_body_ids, d.body_ids[1], next);
+    if (task->variant == PPK_A4 || task->variant == PPK_ALIGN2) add_ids(s->runs, task->body_ids[1], task->num_body_ids, d.body_ids[1], next);
     for (int h = 0; h < 2; ++h) {
       int row = find_row(s->runs, task->paddle_body[h]);
-      if (row < 0 && (h == 0 || task->variant == PPK_A4)) {   // paddle not among the obs bodies: stage it too
+      if (row < 0 && (h == 0 || task->variant == PPK_A4 || task->variant == PPK_ALIGN2)) {   // paddle not among the obs bodies: stage it too
         s->runs.push_back({task->paddle_body[h], 1, next});
         row = next++;
       }
@@ -327,7 +339,7 @@ int ppk_host_session_create(const PpkTask* task, int64_t max_envs, int32_t num_c
   const int A = task->num_actors, D = task->num_dofs;
   const size_t n = (size_t)max_envs;
   const int obs_w = (task->variant == PPK_BASE) ? 24 : (task->variant == PPK_ADOF) ? 313
-                    : (task->variant == PPK_A4) ? 2 * 94 : 80;
+                    : (task->variant == PPK_A4 || task->variant == PPK_ALIGN2) ? 2 * 94 : 80;
   int rc = PPK_OK;
   for (int i = 0; i < kStreams && rc == PPK_OK; ++i)
     if (cudaStreamCreateWithFlags(&s->streams[i], cudaStreamNonBlocking) != cudaSuccess) rc = PPK_ERR_CUDA;
@@ -348,6 +360,7 @@ int ppk_host_session_create(const PpkTask* task, int64_t max_envs, int32_t num_c
   if (rc == PPK_OK) rc = dmalloc(&s->rew, n * 2);
   if (rc == PPK_OK) rc = dmalloc(&s->reset, n);
   if (rc == PPK_OK) rc = dmalloc(&s->progress, n);
+  if (rc == PPK_OK && task->variant == PPK_ALIGN2) rc = dmalloc(&s->last_hitter, n);
   for (int i = 0; i < s->num_flags && rc == PPK_OK; ++i) rc = dmalloc(&s->flags[i], n);
   if (rc == PPK_OK) rc = dmalloc(&s->stats, (size_t)PPK_STATS_SLOTS * PPK_NUM_STATS);
   if (rc == PPK_OK) rc = dmalloc(&s->scratch, 16);
@@ -387,6 +400,7 @@ int ppk_host_post_physics_step(PpkHostSession* s, const PpkBuffers* hb, uint32_t
   if ((rew || rst))
     for (int i = 0; i < s->num_flags; ++i)
       if (!hb->flags[i]) return PPK_ERR_NULL;
+  if (v == PPK_ALIGN2 && (rew || rst) && !hb->last_hitter) return PPK_ERR_NULL;
   if (v == PPK_ADOF && (!hb->initial_body_states || !hb->initial_dof_states || (rst && !hb->reset_ball_pos_yz))) return PPK_ERR_NULL;
 
   // constant tensors (initial states, launch table) go up when their host pointers change
@@ -425,6 +439,7 @@ int ppk_host_post_physics_step(PpkHostSession* s, const PpkBuffers* hb, uint32_t
     bool zc = is_pinned_host(hb->progress_buf) && is_pinned_host(hb->reset_buf) && is_pinned_host(hb->rew_buf) &&
               is_pinned_host(hb->pre_ball_states) && is_pinned_host(hb->root_states) && is_pinned_host(hb->dof_states);
     for (int i = 0; i < s->num_flags; ++i) zc = zc && is_pinned_host(hb->flags[i]);
+    zc = zc && is_pinned_host(hb->last_hitter);
     s->zero_copy = zc;
     s->key = *hb;
     s->key_phases = phases;

@@ -135,6 +135,7 @@ struct ResetArgs {
   int num_flags;               // flags written at reset
   int flag_reset_value[PPK_MAX_FLAGS];
   int variant;
+  long long* last_hitter;      // ALIGN2: back to its initial value 2
 };
 
 __global__ void __launch_bounds__(128)
@@ -175,6 +176,7 @@ reset_idx_kernel(const __grid_constant__ KArgs k, const __grid_constant__ ResetA
   if (lane == 0) {
     k.progress[env] = 0;
     if (base) k.reset[env] = 0;                      // BASE:579
+    if (r.last_hitter != nullptr) r.last_hitter[env] = 2;
   }
   if (lane < r.num_flags) k.flags[lane][env] = (unsigned char)r.flag_reset_value[lane];
   if (r.actor_out != nullptr && lane < k.A) r.actor_out[i * k.A + lane] = (int)r.actor_indices[env * k.A + lane];
@@ -225,9 +227,9 @@ sample_launch_kernel(float* __restrict__ vel, float* __restrict__ pos_yz, const 
                                 make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
   const float rad = 0.017453292519943295f;
   float s, a, z = 0.0f, vx, vy, vz;
-  if (variant == PPK_TILT || variant == PPK_A4 || variant == PPK_ALIGN) {
+  if (variant == PPK_TILT || variant == PPK_A4 || variant == PPK_ALIGN || variant == PPK_ALIGN2) {
     // s = -U(8.0, 8.6 | 8.8), a = U(-5,5) deg, z = U(2,10) deg;  v = s*(cos a cos z, sin a sin z, sin a)
-    s = -(8.0f + u01(r.x) * (variant == PPK_ALIGN ? 0.8f : 0.6f));
+    s = -(8.0f + u01(r.x) * ((variant == PPK_ALIGN || variant == PPK_ALIGN2) ? 0.8f : 0.6f));
     a = (-5.0f + u01(r.y) * 10.0f) * rad;
     z = (2.0f + u01(r.z) * 8.0f) * rad;
     vx = s * cosf(a) * cosf(z); vy = s * sinf(a) * sinf(z); vz = s * sinf(a);

@@ -54,8 +54,8 @@ def sample_ball_launch(cfg: TaskConfig, n: int, g, device) -> torch.Tensor:
     u = lambda lo, hi: torch.rand(n, generator=g, device=device, dtype=torch.float64) * (hi - lo) + lo
     rad = math.pi / 180.0
     v = cfg.variant
-    if v in ("tilt", "a4", "align"):
-        s = -u(8.0, 8.8 if v == "align" else 8.6)
+    if v in ("tilt", "a4", "align", "align2"):
+        s = -u(8.0, 8.8 if v in ("align", "align2") else 8.6)
         a, z = u(-5.0, 5.0) * rad, u(2.0, 10.0) * rad
         out = torch.stack((s * a.cos() * z.cos(), s * a.sin() * z.sin(), s * a.sin()), dim=-1)
     elif v in ("nes", "adof"):
@@ -83,7 +83,7 @@ def make_state(cfg: TaskConfig, num_envs: int, seed: int = 0, device: str = "cpu
     root = _rows(n, A, g, dev, pos_std=0.02)
     # humanoid roots: (0,0,1) and (3.5,0,1) +- noise
     root[:, cfg.humanoid_actor[0], 0:3] = torch.tensor((0.0, 0.0, 1.0), device=dev) + 0.05 * torch.randn(n, 3, generator=g, device=dev)
-    if cfg.variant in ("a4", "base"):
+    if cfg.variant in ("a4", "align2", "base"):
         root[:, cfg.humanoid_actor[1], 0:3] = torch.tensor((3.5, 0.0, 1.0), device=dev) + 0.05 * torch.randn(n, 3, generator=g, device=dev)
     root[:, cfg.ball_actor] = _ball_row(n, g, dev)
     if cfg.variant == "base":
@@ -94,7 +94,7 @@ def make_state(cfg: TaskConfig, num_envs: int, seed: int = 0, device: str = "cpu
     ball_for = {0: cfg.ball_actor}
     if cfg.variant == "base":
         ball_for = {0: 4, 1: 3}           # paddle1<->ball2, paddle2<->ball1 (BASE:634-647)
-    elif cfg.variant == "a4":
+    elif cfg.variant in ("a4", "align2"):
         ball_for = {0: 3, 1: 3}
     for k, ball_row in ball_for.items():
         near = torch.rand(n, generator=g, device=dev) < 0.5
@@ -170,6 +170,8 @@ def make_state(cfg: TaskConfig, num_envs: int, seed: int = 0, device: str = "cpu
         st[name] = torch.rand(n, generator=g, device=dev) < p
     for name in cfg.counter_names:
         st[name] = torch.rand(n, generator=g, device=dev) < 0.25
+    for name in cfg.state_names:          # last_hitter in {1, 2}
+        st[name] = torch.randint(1, 3, (n,), generator=g, device=dev, dtype=torch.int64)
 
     # actions and PD scaling (TILT:666-671: offset/scale = 0.5*(hi +- lo) of the DOF limits)
     lo = -1.0 - torch.rand(D, generator=g, device=dev)
@@ -179,7 +181,7 @@ def make_state(cfg: TaskConfig, num_envs: int, seed: int = 0, device: str = "cpu
     st["actions"] = torch.rand(n, D, generator=g, device=dev) * 2.0 - 1.0
     st["pd_targets"] = torch.zeros(n, D, device=dev)
     st["actor_indices"] = torch.arange(n * A, dtype=torch.int64, device=dev)               # TILT:645
-    dof_per = 2 if cfg.variant == "a4" else 1                                               # A4:889
+    dof_per = 2 if cfg.variant in ("a4", "align2") else 1                                               # A4:889
     st["dof_indices"] = torch.arange(n * dof_per, dtype=torch.int64, device=dev)
 
     if adversarial and n >= 64:
@@ -199,7 +201,7 @@ def _plant_adversarial(cfg: TaskConfig, st: State) -> None:
         c = f32(v)
         return [float(torch.nextafter(c, f32(-1e30))), float(c), float(torch.nextafter(c, f32(1e30)))]
 
-    x_thr = (0.4, 1.06, 1.7, 1.72, 1.78, 1.8, 1.9, 2.2, 2.44, 2.5, 3.1)
+    x_thr = (-3.1, 0.4, 1.06, 1.3, 1.7, 1.72, 1.78, 1.8, 1.9, 2.2, 2.44, 2.5, 3.1)
     y_thr = (-0.6, -0.4, 0.4, 0.6)
     z_thr = (0.1, 0.78, 0.82, 0.83, 0.96, 0.98, 1.14, 1.25)
     for col, thrs in ((0, x_thr), (1, y_thr), (2, z_thr)):
@@ -228,7 +230,7 @@ def _plant_adversarial(cfg: TaskConfig, st: State) -> None:
         if i >= root.shape[0]:
             return
         rb[i, 0, 3:7] = f32(q)
-        if cfg.variant in ("a4", "base") and rb.shape[1] > 40:
+        if cfg.variant in ("a4", "align2", "base") and rb.shape[1] > 40:
             rb[i, 40, 3:7] = f32(q)
         i += 1
     # time-out boundary: progress L-3, L-2 (resets after the +1), L-1

@@ -72,6 +72,9 @@ class PingpongTask(VecTask):
         for name in cfg.counter_names:
             t = sim_state[name].to(dev).clone() if name in sim_state else torch.zeros(n, dtype=torch.bool, device=dev)
             setattr(self, name, t)
+        for name in cfg.state_names:          # ALIGN def #2: last_hitter, initialised to 2 (ALIGN:1253)
+            t = sim_state[name].to(dev).clone() if name in sim_state else torch.full((n,), 2, dtype=torch.int64, device=dev)
+            setattr(self, name, t)
         # saved pre-step ball state: the reference clones the 13-float row (TILT:1020) although only
         # vx (and vz in ALIGN) is read back; by default only those two floats are kept
         width = 13 if full_pre_ball_clone else 2
@@ -102,7 +105,7 @@ class PingpongTask(VecTask):
         if self.envelope and "actor_indices" in self.st and "dof_indices" in self.st:
             d.update(reset_count=self.reset_count, reset_actor_indices=self.reset_actor_indices,
                      reset_dof_indices=self.reset_dof_indices)
-        for name in self.cfg.flag_names + self.cfg.counter_names:
+        for name in self.cfg.flag_names + self.cfg.counter_names + self.cfg.state_names:
             d[name] = getattr(self, name)
         return d
 
@@ -222,6 +225,10 @@ class HumanoidPingpongAlignment(PingpongTask):     # tasks/humanoid_pingpong_ali
     variant = "align"
 
 
+class HumanoidPingpongAlignmentTwoHumanoid(PingpongTask):   # tasks/humanoid_pingpong_alignment.py:1233 (reward definition #2)
+    variant = "align2"
+
+
 class HumanoidPingpongTiltNESSparse27DOF(PingpongTask):   # tasks/humanoid_pingpong_3_actor_all_dof.py:65
     variant = "adof"
 
@@ -235,6 +242,7 @@ isaacgym_task_map = {
     "Humanoid12PingpongTiltG1": Humanoid12PingpongTilt,
     "HumanoidPingpongAlignmentG1": HumanoidPingpongAlignment,
     "HumanoidPingpongTiltNESSparse27DOFG1": HumanoidPingpongTiltNESSparse27DOF,
+    "HumanoidPingpongAlignmentTwoHumanoidG1": HumanoidPingpongAlignmentTwoHumanoid,
 }
 VARIANT_CLASS = {c.variant: c for c in isaacgym_task_map.values()}
 

@@ -2,7 +2,7 @@
 
 Run in the build container (needs /root/reference):
 
-    python -m oracle.make_golden            # writes tests/golden/<variant>.npz
+    python -m oracle.make_golden [variant ...]   # writes tests/golden/<variant>.npz (default: all)
 
 For each task variant a small seeded synthetic state (inputs included in the
 fixture, so it is self-contained) is pushed through the reference's
@@ -33,7 +33,10 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     ref = task_oracle.ReferenceImpl()
     torch.set_num_threads(1)
+    only = set(sys.argv[1:])
     for variant, cfg in CONFIGS.items():
+        if only and variant not in only:
+            continue
         st_in = make_state(cfg, NUM_ENVS, seed=SEED + cfg.variant_id)
         st = clone_state(st_in)
         if variant != "base":
@@ -45,7 +48,7 @@ def main():
         out["out__obs_buf"] = obs.numpy()
         out["out__rew_buf"] = st["rew_buf"].numpy()
         out["out__reset_buf"] = st["reset_buf"].numpy()
-        for name in cfg.flag_names + cfg.counter_names:
+        for name in cfg.flag_names + cfg.counter_names + cfg.state_names:
             out["out__" + name] = st[name].numpy()
         path = os.path.join(GOLDEN_DIR, f"{variant}.npz")
         np.savez_compressed(path, **out)

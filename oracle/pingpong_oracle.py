@@ -234,6 +234,42 @@ def align_reward(humanoid_root, paddle, pre_ball, ball, dof_force, dof_vel, rese
     return reward, _reset_mask(bpos[..., 2], 0.1, progress_buf, reset_buf, max_episode_length)
 
 
+def align2_reward(h1_root, paddle1, h2_root, paddle2, pre_ball, ball, dof_force, dof_vel, reset_buf, progress_buf,
+                  max_episode_length, alpha, power_coefficient, penalty, hit_table_reward, not_hit_table_penalty,
+                  reward_calculated, last_hitter):
+    """ALIGN:1233-1351, the two-humanoid definition (never live in the reference: defect D7; it loads
+    once its return annotation is repaired, `ref_extract.load_align_two_humanoid_reward`).  TorchScript:
+    `reward_calculated |= ...` stays local to the call (D16); `last_hitter` is returned."""
+    reward_calculated = reward_calculated.clone()
+    bpos = ball[..., 0:3]
+    bx = bpos[:, 0]
+    pre_vx, pre_vz, vx, vz = pre_ball[..., 7], pre_ball[..., 9], ball[..., 7], ball[..., 9]
+    zero = torch.zeros_like(vx)
+    d1, d2 = _dist3(paddle1[..., 0:3], bpos), _dist3(paddle2[..., 0:3], bpos)
+    pos1, pos2 = 1.0 / (1.0 + 1.5 * d1 * d1), 1.0 / (1.0 + 1.5 * d2 * d2)
+    c1 = (pre_vx < 0) & (vx > 0)                              # humanoid 1 hit the ball
+    c2 = (pre_vx > 0) & (vx < 0)                              # humanoid 2 hit the ball
+    vel1 = torch.where(c1, alpha * torch.abs(vx), zero)
+    vel2 = torch.where(c2, alpha * torch.abs(vx), zero)
+    range1 = (bx > 2.2) & (bx < 3.1)                          # humanoid 2's half of the table
+    range2 = (bx < 1.3) & (bx > 0.4)                          # humanoid 1's half
+    bounce_up = (pre_vz < 0) & (vz > 0)
+    hit1 = torch.where(range1 & bounce_up & (last_hitter == 1) & ~reward_calculated, hit_table_reward, zero)
+    hit2 = torch.where(range2 & bounce_up & (last_hitter == 2) & ~reward_calculated, hit_table_reward, zero)
+    reward_calculated |= (range1 & bounce_up) | (range2 & bounce_up)
+    hit1 = torch.where((bx >= 3.1) & (last_hitter == 1) & ~reward_calculated, not_hit_table_penalty, hit1)
+    hit2 = torch.where((bx <= -3.1) & (last_hitter == 2) & ~reward_calculated, not_hit_table_penalty, hit2)
+    power_reward = _power_reward(dof_force, dof_vel, power_coefficient)
+    r1 = pos1 + power_reward + vel1 + hit1
+    r2 = pos2 + power_reward + vel2 + hit2
+    r1 = torch.where(bx < h1_root[..., 0] - 0.05, r1 + penalty, r1)
+    r2 = torch.where(bx > h2_root[..., 0] + 0.05, r2 + penalty, r2)
+    reset = _reset_mask(bpos[..., 2], 0.1, progress_buf, reset_buf, max_episode_length)
+    last_hitter = torch.where(c1, torch.ones_like(last_hitter), last_hitter)
+    last_hitter = torch.where(c2, torch.full_like(last_hitter, 2), last_hitter)
+    return r1, r2, reset, last_hitter
+
+
 def adof_gradient_penalty(ball_pos, vx, hit_table_reward, not_hit_table_penalty, hit_table_calculated,
                           hit_table_count, humanoid_die_calculated):
     """ADOF:1245-1301."""
@@ -340,8 +376,8 @@ def sample_ball_velocity(rng, variant):
     (TILT:307-318, NES:312-323, ADOF:357-367, A3:300-302, BASE:250-266)."""
     u = rng.uniform
     rad = math.radians
-    if variant in ("tilt", "a4", "align"):
-        s = -u(8.0, 8.8 if variant == "align" else 8.6)
+    if variant in ("tilt", "a4", "align", "align2"):
+        s = -u(8.0, 8.8 if variant in ("align", "align2") else 8.6)
         a = u(-5.0, 5.0)
         z = u(2.0, 10.0)
         return (s * math.cos(rad(a)) * math.cos(rad(z)), s * math.sin(rad(a)) * math.sin(rad(z)), s * math.sin(rad(a)))
@@ -370,6 +406,10 @@ VARIANTS = {
                                            ("no_bounce_before_half_mask", True),
                                            ("reward_calculated_2", False), ("condition_calculated_2", False),
                                            ("no_bounce_before_half_mask_2", True)), reset_dof=True, log_every=40),
+    # ALIGN def #2 has no class code of its own: reward_calculated is cleared like ALIGN:897, and a fresh
+    # rally starts with last_hitter = 2, its documented initial value (ALIGN:1253)
+    "align2": dict(actors=4, ball=3, flags=(("reward_calculated", False),), reset_dof=True, log_every=40,
+                   states=(("last_hitter", 2),)),
     "adof":  dict(actors=3, ball=2, flags=(("paddle_condition_calculated", False), ("die_penalty_calculated", False),
                                            ("humanoid_die_calculated", False), ("hit_table_calculated", False)),
                   reset_dof=True, log_every=32),
@@ -401,6 +441,8 @@ def reset_idx(variant, st, env_ids, ball_vel, ball_pos_yz=None):
     dof_indices = st["dof_indices"].view(n, dof_per)[env_ids].flatten().to(torch.int32)
     st["progress_buf"][env_ids] = 0
     for name, val in v["flags"]:
+        st[name][env_ids] = val
+    for name, val in v.get("states", ()):
         st[name][env_ids] = val
     return actor_indices, dof_indices
 

@@ -77,7 +77,7 @@ def _function_sources(alias):
     return out
 
 
-def load(alias, name, occurrence=0, extra_globals=None):
+def load(alias, name, occurrence=0, extra_globals=None, patch=None):
     """Return reference function `name` of file `alias`.
 
     `occurrence` selects among same-named top-level definitions (ALIGN defines
@@ -97,9 +97,16 @@ def load(alias, name, occurrence=0, extra_globals=None):
     if occurrence >= len(matches):
         raise KeyError(f"{alias}:{name}#{occurrence} not found")
     _, lineno, src = matches[occurrence]
+    if patch is not None:
+        # a documented one-token repair of reference text that cannot load as shipped (e.g. the wrong
+        # return annotation of ALIGN:1233-1254, defect D7); everything else stays the reference's own text
+        old_text, new_text = patch
+        assert src.count(old_text) == 1, "patch must match exactly once"
+        src = src.replace(old_text, new_text)
+        key = key + (new_text,)
     if _tmpdir is None:
         _tmpdir = tempfile.mkdtemp(prefix="ppk_ref_")
-    modname = f"_ppkref_{alias}_{name}_{occurrence}"
+    modname = f"_ppkref_{alias}_{name}_{occurrence}" + ("_patched" if patch is not None else "")
     fpath = os.path.join(_tmpdir, modname + ".py")
     pre = ""
     if extra_globals:
@@ -119,6 +126,14 @@ def load(alias, name, occurrence=0, extra_globals=None):
 
 
 _EXTRA = {}
+
+
+def load_align_two_humanoid_reward():
+    """ALIGN:1233-1351, the second `compute_pingpong_reward` (two humanoids, `last_hitter`).  As shipped
+    it does not compile: the type comment promises a 2-tuple and the body returns four tensors (defect
+    D7).  The return annotation is the only thing repaired here."""
+    return load("ALIGN", "compute_pingpong_reward", 1,
+                patch=("-> Tuple[Tensor, Tensor]", "-> Tuple[Tensor, Tensor, Tensor, Tensor]"))
 
 
 def load_adof_reward():

@@ -29,6 +29,7 @@ class OracleImpl:
     nes_reward = staticmethod(O.nes_reward)
     align_reward = staticmethod(O.align_reward)
     adof_reward = staticmethod(O.adof_reward)
+    align2_reward = staticmethod(O.align2_reward)
 
     @staticmethod
     def pingpong_observations(body_states, ids, ball, adof=False):
@@ -55,6 +56,7 @@ class ReferenceImpl:
         self.nes_reward = ld("NES", "compute_pingpong_reward_only_paddle")
         self.align_reward = ld("ALIGN", "compute_pingpong_reward", 0)
         self._adof = R.load_adof_reward()
+        self.align2_reward = R.load_align_two_humanoid_reward()
 
     def pingpong_observations(self, body_states, ids, ball, adof=False):
         return (self._pp_obs_adof if adof else self._pp_obs)(body_states, ids, ball)
@@ -83,7 +85,7 @@ def compute_observations(cfg, st, impl=OracleImpl):
         p1, p2 = rb[:, cfg.paddle_body[0], :], rb[:, cfg.paddle_body[1], :]
         return impl.base_observations(st["obs_buf"], p1, p2, p1, p2, root[:, 3, :], root[:, 4, :])
     ball = root[:, cfg.ball_actor, :]
-    if v == "a4":
+    if v in ("a4", "align2"):
         rows = []
         for ids in (cfg.body_ids, cfg.body_ids_2):
             ids = _ids(ids)
@@ -143,6 +145,13 @@ def compute_reward(cfg, st, impl=OracleImpl):
                                        st["reward_calculated_2"], st["no_bounce_before_half_mask_2"])
         assert torch.equal(rst, rst2)
         rew = torch.stack((rew1, rew2), dim=-1)
+    elif v == "align2":
+        r1, r2, rst, lh = impl.align2_reward(
+            h_root, paddle, root[:, cfg.humanoid_actor[1], :], rb[:, cfg.paddle_body[1], :], pre_ball, ball, force,
+            dof_vel, reset_buf, progress, L, _f(cfg.alpha), _f(cfg.power_coefficient), _f(cfg.penalty),
+            _f(cfg.hit_table_reward), _f(cfg.not_hit_table_penalty), st["reward_calculated"], st["last_hitter"])
+        rew = torch.stack((r1, r2), dim=-1)
+        st["last_hitter"][:] = lh            # the caller keeps the returned tensor
     elif v == "adof":
         init_dof = st["initial_dof_states"]
         out = impl.adof_reward(

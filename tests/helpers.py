@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-VARIANTS = ("base", "a3", "tilt", "nes", "align", "a4", "adof")
+VARIANTS = ("base", "a3", "tilt", "nes", "align", "a4", "adof", "align2")
 
 
 def load_golden(variant):

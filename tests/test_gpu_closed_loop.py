@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("variant", ["tilt", "nes", "a4", "adof"])
+@pytest.mark.parametrize("variant", ["tilt", "nes", "a4", "adof", "align2"])
 def test_sixty_steps_keep_every_invariant(variant):
     cfg = CONFIGS[variant]
     n = 4096

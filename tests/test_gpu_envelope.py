@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("variant", ["a3", "tilt", "nes", "align", "a4", "adof"])
+@pytest.mark.parametrize("variant", ["a3", "tilt", "nes", "align", "a4", "adof", "align2"])
 def test_fused_step_emits_reset_index_lists_and_timeouts(variant):
     cfg = CONFIGS[variant]
     n = 3000

@@ -51,7 +51,7 @@ def test_golden_vectors(variant):
         run(cfg, g, N.PHASE_PROGRESS | N.PHASE_REWARD | N.PHASE_OBS)
     assert_close_fields(cfg, g["obs_buf"], outs["obs_buf"], g["rew_buf"], outs["rew_buf"], f"golden[{variant}]")
     assert torch.equal(g["reset_buf"].cpu(), outs["reset_buf"])
-    assert_exact(cfg, g, outs, cfg.flag_names + cfg.counter_names, f"golden[{variant}]")
+    assert_exact(cfg, g, outs, cfg.flag_names + cfg.counter_names + cfg.state_names, f"golden[{variant}]")
 
 
 def oracle_full_step(cfg, st):
@@ -85,7 +85,7 @@ def test_fused_step_matches_oracle(variant, n, seed):
     g = gpu_state(st)
     run(cfg, g, N.PHASE_ALL)
     ctx = f"{variant} n={n}"
-    assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names, ctx)
+    assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, ctx)
     assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], ctx)
     # statistics: fp64 partial sums on the device vs fp64 oracle sums
     got = g["stats"].sum(dim=0).cpu()
@@ -113,7 +113,7 @@ def test_unfused_reference_call_sequence_equals_fused(variant):
     a.post_physics_step()
     b.post_physics_step()
     torch.cuda.synchronize()
-    for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf") + cfg.flag_names + cfg.counter_names:
+    for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf") + cfg.flag_names + cfg.counter_names + cfg.state_names:
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert torch.equal(a.root_states, b.root_states) and torch.equal(a.vec_dof_states, b.vec_dof_states)
 
@@ -152,7 +152,7 @@ def test_multi_step_trajectory(variant):
         task.post_physics_step()
         torch.cuda.synchronize()
         ctx = f"{variant} step {step}"
-        for name in ("reset_buf", "progress_buf") + cfg.flag_names + cfg.counter_names:
+        for name in ("reset_buf", "progress_buf") + cfg.flag_names + cfg.counter_names + cfg.state_names:
             assert torch.equal(getattr(task, name).cpu(), o[name]), f"{ctx}: {name}"
         assert torch.equal(task.root_states.cpu(), o["root_states"]), ctx
         assert torch.equal(task.vec_dof_states.cpu(), o["dof_states"]), ctx
@@ -171,7 +171,7 @@ def test_ragged_sizes(variant, n):
     # guard rows after the tensors: nothing beyond N may be written (compute-sanitizer is closed on
     # this pool, so out-of-bounds stores are caught with sentinels instead)
     guarded = {}
-    for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names + cfg.counter_names:
+    for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names + cfg.counter_names + cfg.state_names:
         t = g[name]
         big = torch.empty((n + 8,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         if t.dtype == torch.bool:
@@ -186,7 +186,7 @@ def test_ragged_sizes(variant, n):
         tail = big[n:]
         ok = bool(tail.all()) if big.dtype == torch.bool else bool((tail == -777).all())
         assert ok, f"{variant} n={n}: {name} was written past its end"
-    assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names, f"{variant} n={n}")
+    assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, f"{variant} n={n}")
     assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], f"{variant} n={n}")
 
 
@@ -319,7 +319,7 @@ def test_host_session_equals_device_path(variant, pin):
         for step in range(4):
             sess.post_physics_step(N.PHASE_ALL & ~N.PHASE_STATS)
             run(cfg, dev, N.PHASE_ALL & ~N.PHASE_STATS)
-            for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names + cfg.counter_names:
+            for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names + cfg.counter_names + cfg.state_names:
                 assert torch.equal(sess.state[name], dev[name].cpu()), f"{variant} step {step}: {name}"
         h2d, d2h = sess.traffic()
         assert h2d > 0 and d2h > 0

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("variant", ["a3", "tilt", "nes", "align", "a4", "adof"])
+@pytest.mark.parametrize("variant", ["a3", "tilt", "nes", "align", "a4", "adof", "align2"])
 def test_sampler_matches_reference_distribution(variant):
     cfg = CONFIGS[variant]
     n = 40000
@@ -102,5 +102,5 @@ def test_unaligned_shard_takes_the_generic_path(variant):
         g["progress_buf"] = g["progress_buf"].clone()      # int64 views at odd offsets are still 8-byte aligned
         N.check(lib.ppk_post_physics_step(N.make_task(cfg), N.make_buffers(cfg, g), N.PHASE_ALL, N.current_stream_ptr()), "step")
     torch.cuda.synchronize()
-    for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names + cfg.counter_names:
+    for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names + cfg.counter_names + cfg.state_names:
         assert torch.equal(view[name], copy[name]), name

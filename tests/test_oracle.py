@@ -27,7 +27,7 @@ def test_oracle_matches_golden(variant):
     torch.testing.assert_close(obs, outs["obs_buf"], rtol=3e-7, atol=1e-7)
     torch.testing.assert_close(st["rew_buf"], outs["rew_buf"], rtol=3e-7, atol=1e-4)
     assert torch.equal(st["reset_buf"], outs["reset_buf"])
-    for name in cfg.flag_names + cfg.counter_names:
+    for name in cfg.flag_names + cfg.counter_names + cfg.state_names:
         assert torch.equal(st[name], outs[name]), name
 
 
