@@ -187,6 +187,11 @@ typedef struct PpkBuffers {
   /* ALIGN2 only: who hit the ball last, 1 or 2 (ALIGN:1253, returned by the reward ALIGN:1349-1351;
    * read + written; a reset puts it back to its initial value 2) */
   int64_t* last_hitter;
+  /* ADOF, optional: the imitation reference pose repacked once at init as [N, n_balance, 6] =
+   * initial_body_states[:, balance_ids][..., (0,1,2,7,8,9)] (what ADOF:1345-1349, 1908-1909 read of it).
+   * When non-NULL the step reads this instead of initial_body_states (552 B per env instead of 28
+   * rigid-body rows); the caller keeps it in sync if it ever rewrites the reference pose. */
+  const float* initial_balance_states;
 } PpkBuffers;
 
 PPK_API int ppk_abi_version(void);

@@ -52,7 +52,7 @@ class PpkBuffers(C.Structure):
         ("clip_actions", C.c_float), ("dof_indices_per_env", C.c_int32), ("timeout_buf", C.c_void_p),
         ("actor_indices", C.c_void_p), ("dof_indices", C.c_void_p), ("reset_count", C.c_void_p),
         ("reset_actor_indices", C.c_void_p), ("reset_dof_indices", C.c_void_p),
-        ("last_hitter", C.c_void_p),
+        ("last_hitter", C.c_void_p), ("initial_balance_states", C.c_void_p),
     ]
 
 
@@ -190,6 +190,7 @@ def make_buffers(cfg: TaskConfig, st: dict, host: bool = False) -> PpkBuffers:
     b.initial_root_states = get("initial_root_states", f32, (n, A, 13))
     b.initial_dof_states = get("initial_dof_states", f32, (n, D, 2))
     b.initial_body_states = get("initial_body_states", f32, (n, B, 13))
+    b.initial_balance_states = get("initial_balance_states", f32, (n, len(cfg.balance_ids), 6))
     rbv = st.get("reset_ball_vel")
     b.reset_ball_vel = _ptr(rbv, f32, "reset_ball_vel", host)
     b.reset_ball_pos_yz = get("reset_ball_pos_yz", f32, (n, 2))

@@ -7,7 +7,10 @@
 //   stage      1-D bulk async copies (cp.async.bulk / TMA engine) on one mbarrier: per env the
 //              16-byte aligned windows around its live rows (2096 B) and reference rows (1472 B),
 //              per tile the contiguous root / DOF / reference-DOF / force slices.  Tail tiles and
-//              misaligned tensors take an LDG path into the same layout.
+//              misaligned tensors take an LDG path into the same layout.  COMPACT: the reference pose
+//              is a constant of the task (ADOF:196-200), so the caller may hand it over repacked once
+//              at init as [N,23,6] (pos, linvel of the balance bodies): 552 B per env in one bulk
+//              copy per tile instead of a 1472 B window per env.
 //   warps 1-4  one env per pass, lane = balance body (23) and lane = DOF (27): imitation diffs, the
 //              seven per-env reductions of compute_imitation_reward (ADOF:1313-1418) in one fused
 //              butterfly, heading frame, imitation observation segments (ADOF:1891-1927) and the ten
@@ -32,11 +35,12 @@ constexpr int kAdofRbRows = 40;  // rows 0..39 staged from the live tensor
 constexpr int kAdofInitRows = 28;  // rows 0..27 staged from the reference pose
 constexpr int kAdofObs = 6 * kAdofJ + 2 * kAdofD + 7 + 6 * kAdofNB + 2 * kAdofD;   // 313
 
+template <bool COMPACT>
 struct AdofLayout {
   static constexpr int kRbEnv = kAdofRbRows * kRow;      // 520 floats used
-  static constexpr int kInitEnv = kAdofInitRows * kRow;  // 364
+  static constexpr int kInitEnv = COMPACT ? kAdofNB * 6 : kAdofInitRows * kRow;  // 138 | 364
   static constexpr int kSRb = ((kRbEnv + 3 + 3) / 4) * 4;      // 524: window incl. alignment slack
-  static constexpr int kSInit = ((kInitEnv + 3 + 3) / 4) * 4;  // 368
+  static constexpr int kSInit = COMPACT ? kInitEnv : ((kInitEnv + 3 + 3) / 4) * 4;  // 138 (dense) | 368
   static constexpr int kRoot = 3 * kRow;                 // 39, dense
   static constexpr int kDof = 2 * kAdofD;                // 54, dense
   static constexpr int kSHdr = 24;
@@ -67,9 +71,10 @@ __device__ __forceinline__ void adof_wait() { asm volatile("bar.sync 2, %0;" ::"
 
 constexpr uint32_t kPhaseDeferCounterClear = 1u << 8;   // internal (host session): clear counters once per shard
 
-__global__ void __launch_bounds__(kAdofThreads, kAdofThreads <= 96 ? 10 : 6)
+template <bool COMPACT>
+__global__ void __launch_bounds__(kAdofThreads, 6)
 adof_step_kernel(const __grid_constant__ KArgs k) {
-  using L = AdofLayout;
+  using L = AdofLayout<COMPACT>;
   extern __shared__ __align__(128) float smem[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -89,12 +94,13 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
   const bool bulk = k.bulk_ok && (nvalid == T);
   const int env_stride = k.B * kRow;
   const float* g_rb = k.rb + (size_t)env0 * env_stride;
-  const float* g_init = k.init_rb + (size_t)env0 * env_stride;
+  const float* g_init = COMPACT ? k.init_bal + (size_t)env0 * L::kInitEnv : k.init_rb + (size_t)env0 * env_stride;
 
   // position of env e's row 0 inside its 16-byte aligned staging window (floats)
   const int off_rb0 = (int)((reinterpret_cast<uintptr_t>(g_rb) & 15u) >> 2);
   const int off_init0 = (int)((reinterpret_cast<uintptr_t>(g_init) & 15u) >> 2);
   auto win_off = [&](const float* base, int e) -> int {
+    if (COMPACT && base != g_rb) return 0;
     return bulk ? (((base == g_rb ? off_rb0 : off_init0) + e * env_stride) & 3) : 0;
   };
 
@@ -111,6 +117,7 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
       bulk_g2s(dof_s, k.dof + (size_t)env0 * L::kDof, 4u * T * L::kDof, bar);
       bulk_g2s(idof_s, k.init_dof + (size_t)env0 * L::kDof, 4u * T * L::kDof, bar);
       bulk_g2s(force_s, k.force + (size_t)env0 * D, 4u * T * D, bar);
+      if (COMPACT) bulk_g2s(init_s, g_init, 4u * T * L::kInitEnv, bar);
     }
     if (warp >= 1) {       // 16 windows, four per reducing warp: warp-uniform addresses, one elected lane issues
       const int wu = __shfl_sync(0xffffffffu, warp, 0);
@@ -121,7 +128,7 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
         const uintptr_t a_in = reinterpret_cast<uintptr_t>(g_init + (size_t)e * env_stride) & ~(uintptr_t)15;
         if (elect_one()) {
           bulk_g2s(rb_s + e * L::kSRb, reinterpret_cast<const void*>(a_rb), 4u * L::kSRb, bar);
-          bulk_g2s(init_s + e * L::kSInit, reinterpret_cast<const void*>(a_in), 4u * L::kSInit, bar);
+          if (!COMPACT) bulk_g2s(init_s + e * L::kSInit, reinterpret_cast<const void*>(a_in), 4u * L::kSInit, bar);
         }
       }
     }
@@ -132,7 +139,7 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
     }
     for (int f = threadIdx.x; f < T * L::kInitEnv; f += kAdofThreads) {
       const int e = f / L::kInitEnv, r = f - e * L::kInitEnv;
-      init_s[e * L::kSInit + r] = (e < nvalid) ? g_init[(size_t)e * env_stride + r] : 0.0f;
+      init_s[e * L::kSInit + r] = (e < nvalid) ? g_init[(size_t)e * (COMPACT ? L::kInitEnv : env_stride) + r] : 0.0f;
     }
     for (int f = threadIdx.x; f < T * L::kRoot; f += kAdofThreads)
       root_s[f] = (f < nvalid * L::kRoot) ? k.root[(size_t)env0 * L::kRoot + f] : 0.0f;
@@ -168,11 +175,12 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
       const float* rb_e = rb_s + e * L::kSRb + win_off(g_rb, e);
       const float* in_e = init_s + e * L::kSInit + win_off(g_init, e);
       const float* cur = rb_e + bal_id * kRow;
-      const float* ref = in_e + bal_id * kRow;
       const bool body_on = lane < NB;
+      const float* ref = COMPACT ? in_e + (body_on ? lane : 0) * 6 : in_e + bal_id * kRow;
+      const float* refv = ref + (COMPACT ? 3 : 7);
       // imitation diffs: ref - cur (ADOF:1345,1349 / ADOF:1908-1909)
       float dpx = ref[0] - cur[0], dpy = ref[1] - cur[1], dpz = ref[2] - cur[2];
-      float dvx = ref[7] - cur[7], dvy = ref[8] - cur[8], dvz = ref[9] - cur[9];
+      float dvx = refv[0] - cur[7], dvy = refv[1] - cur[8], dvz = refv[2] - cur[9];
       // has_fallen uses cur - ref (ADOF:1412)
       float nx = cur[0] - ref[0], ny = cur[1] - ref[1], nz = cur[2] - ref[2];
       // per-body sums of squares; the /3 of the inner mean is applied once per env in phase R
@@ -440,17 +448,21 @@ inline int launch_adof(const KArgs& k0, cudaStream_t s) {
   if (k.B < kAdofRbRows) return PPK_ERR_SHAPE;
   for (int j = 0; j < kAdofJ; ++j)
     if (k.ids[0][j] >= kAdofRbRows) return PPK_ERR_SHAPE;
+  const bool compact = k.init_bal != nullptr;
   for (int j = 0; j < kAdofNB; ++j)
-    if (k.bal_ids[j] >= kAdofInitRows) return PPK_ERR_SHAPE;
+    if (k.bal_ids[j] >= (compact ? kAdofRbRows : kAdofInitRows)) return PPK_ERR_SHAPE;
   if (k.paddle_body[0] >= kAdofRbRows || k.pelvis_body >= kAdofRbRows) return PPK_ERR_SHAPE;
-  const void* al[] = {k.rb, k.init_rb, k.root, k.dof, k.init_dof, k.force};
+  const void* al[] = {k.rb, compact ? (const void*)k.init_bal : (const void*)k.init_rb, k.root, k.dof, k.init_dof, k.force};
   bool bulk = k.B > kAdofRbRows;
   for (const void* p : al) bulk = bulk && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
   k.bulk_ok = bulk ? 1 : 0;
-  constexpr size_t smem = (size_t)AdofLayout::kFloats * sizeof(float);
+  const size_t smem = (size_t)(compact ? AdofLayout<true>::kFloats : AdofLayout<false>::kFloats) * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(adof_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(adof_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(AdofLayout<false>::kFloats * sizeof(float))) != cudaSuccess ||
+        cudaFuncSetAttribute(adof_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(AdofLayout<true>::kFloats * sizeof(float))) != cudaSuccess) {
       cudaGetLastError();
       return PPK_ERR_LAUNCH;
     }
@@ -458,7 +470,8 @@ inline int launch_adof(const KArgs& k0, cudaStream_t s) {
   }
   const bool fused_reset = (k.phases & PPK_PHASE_RESET) != 0 && !(k.phases & kPhaseDeferCounterClear);
   const long long tiles = (k.n + kAdofTile - 1) / kAdofTile;
-  adof_step_kernel<<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
+  if (compact) adof_step_kernel<true><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
+  else adof_step_kernel<false><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
   if (cudaGetLastError() != cudaSuccess) return PPK_ERR_LAUNCH;
   if (fused_reset) return launch_adof_clear(k.scratch, k.flags, k.n, s);
   return PPK_OK;

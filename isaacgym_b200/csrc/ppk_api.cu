@@ -24,6 +24,7 @@ int fill_args(const PpkTask* t, const PpkBuffers* b, uint32_t phases, KArgs* k) 
   memset(k, 0, sizeof(*k));
   k->rb = b->rigid_body_states; k->root = b->root_states; k->dof = b->dof_states; k->force = b->dof_forces;
   k->last_hitter = reinterpret_cast<long long*>(b->last_hitter);
+  k->init_bal = b->initial_balance_states;
   k->timeout = reinterpret_cast<long long*>(b->timeout_buf);
   if (b->reset_count != nullptr) {
     if (!b->actor_indices || !b->reset_actor_indices || b->dof_indices_per_env < 0 ||
@@ -118,7 +119,7 @@ int check_step_pointers(const PpkTask* t, const PpkBuffers* b, uint32_t phases) 
   if (rst && (!b->initial_root_states || !b->reset_ball_vel)) return PPK_ERR_NULL;
   if (rst && t->reset_dof && !b->initial_dof_states) return PPK_ERR_NULL;
   if (v == PPK_ADOF) {
-    if (!b->initial_body_states || !b->initial_dof_states) return PPK_ERR_NULL;
+    if ((!b->initial_body_states && !b->initial_balance_states) || !b->initial_dof_states) return PPK_ERR_NULL;
     if (rst && (!b->reset_ball_pos_yz || !b->scratch)) return PPK_ERR_NULL;
   }
   if (v == PPK_ALIGN2 && (rew || rst) && !b->last_hitter) return PPK_ERR_NULL;

@@ -25,6 +25,7 @@ struct KArgs {
   const float* init_root;
   const float* init_dof;
   const float* init_rb;
+  const float* init_bal;     // optional compact reference pose [N, n_balance, 6]
   const float* reset_vel;
   const float* reset_yz;
   float* obs;

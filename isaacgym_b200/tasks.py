@@ -25,13 +25,22 @@ _STATE_KEYS = ("rigid_body_states", "root_states", "dof_states", "dof_forces", "
                "pd_action_offset", "pd_action_scale", "actor_indices", "dof_indices")
 
 
+def pack_reference_pose(cfg: TaskConfig, initial_body_states: torch.Tensor) -> torch.Tensor:
+    """initial_body_states[:, balance_ids][..., (0,1,2,7,8,9)] as one contiguous [N, n_balance, 6] tensor --
+    everything compute_imitation_reward / compute_imitation_observations read of the reference pose
+    (ADOF:1345-1349, ADOF:1908-1909).  `PpkBuffers.initial_balance_states`."""
+    ids = torch.tensor(cfg.balance_ids, dtype=torch.long, device=initial_body_states.device)
+    rows = initial_body_states[:, ids]
+    return torch.cat([rows[..., 0:3], rows[..., 7:10]], dim=-1).contiguous()
+
+
 class PingpongTask(VecTask):
     """Generic task over one variant; the named subclasses below only pick the variant."""
     variant = "tilt"
 
     def __init__(self, sim_state: Dict[str, torch.Tensor], cfg: Optional[TaskConfig] = None,
                  device: str = "cuda:0", fused: bool = True, full_pre_ball_clone: bool = False,
-                 log_stats: bool = False, envelope: bool = False, **kw):
+                 log_stats: bool = False, envelope: bool = False, compact_reference_pose: bool = True, **kw):
         cfg = cfg or CONFIGS[self.variant]
         n = sim_state["root_states"].shape[0]
         super().__init__(cfg, n, device=device, **kw)
@@ -49,6 +58,10 @@ class PingpongTask(VecTask):
         for key in _STATE_KEYS:
             if key in sim_state:
                 self.st[key] = sim_state[key].to(dev).contiguous()
+        if cfg.balance_ids and "initial_body_states" in self.st and compact_reference_pose:
+            # the imitation reference pose is a constant of the task (ADOF:196-200): repack the fields
+            # the step reads of it once, [N,23,6] = (pos, linvel) of the balance bodies
+            self.st["initial_balance_states"] = pack_reference_pose(cfg, self.st["initial_body_states"])
         self.root_states = self.st["root_states"]
         self.vec_root_states = self.root_states
         self.body_states = self.st["rigid_body_states"]

@@ -325,3 +325,23 @@ def test_host_session_equals_device_path(variant, pin):
         assert h2d > 0 and d2h > 0
     finally:
         sess.close()
+
+
+@pytest.mark.parametrize("n", [4096, 1001, 5])
+def test_adof_compact_reference_pose(n):
+    """PpkBuffers.initial_balance_states (the reference pose repacked once at init, [N,23,6]) gives the
+    same bits as reading the 28 reference rows of initial_body_states, and matches the oracle."""
+    from isaacgym_b200.tasks import pack_reference_pose
+    cfg = CONFIGS["adof"]
+    st = make_state(cfg, n, seed=77)
+    want, _ = oracle_full_step(cfg, st)
+    full = gpu_state(st)
+    run(cfg, full, N.PHASE_ALL)
+    comp = gpu_state(st)
+    comp["initial_balance_states"] = pack_reference_pose(cfg, comp["initial_body_states"])
+    del comp["initial_body_states"]                      # the compact tensor alone is enough
+    run(cfg, comp, N.PHASE_ALL)
+    for name in ("obs_buf", "rew_buf") + STATE_EXACT + cfg.flag_names + cfg.counter_names:
+        assert torch.equal(comp[name], full[name]), name
+    assert_exact(cfg, comp, want, STATE_EXACT + cfg.flag_names + cfg.counter_names, f"adof compact n={n}")
+    assert_close_fields(cfg, comp["obs_buf"], want["obs_buf"], comp["rew_buf"], want["rew_buf"], f"adof compact n={n}")
