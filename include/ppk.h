@@ -252,6 +252,48 @@ PPK_API int ppk_host_post_physics_step(PpkHostSession* s, const PpkBuffers* host
 /* bytes moved by the last call */
 PPK_API int ppk_host_session_traffic(const PpkHostSession* s, int64_t* h2d_bytes, int64_t* d2h_bytes);
 
+/* ---- learner side of the path: input normalisation + first MLP layer ----
+ * rl_games `normalize_input: True` (cfg/train/HumanoidPingpongTiltG1PPO.yaml:51) = RunningMeanStd
+ * (rl_games/algos_torch/running_mean_std.py; un-vendored, restated in oracle/policy_oracle.py):
+ * fp64 running_mean / running_var [width] and count [1], epsilon 1e-5, output clamped to +-5.
+ * `clip_obs` is VecTask.step's clamp of obs_buf (clipObservations; <= 0 = none = upstream default inf).
+ * `moments` is a caller-owned, zero-initialised fp64 scratch of 2*width entries (column sums and sums
+ * of squares of the batches not yet merged). */
+typedef struct PpkRunningMeanStd {
+  uint32_t struct_size;
+  int32_t width;
+  float epsilon;
+  float clip_obs;
+  double* running_mean;
+  double* running_var;
+  double* count;
+  double* moments;
+} PpkRunningMeanStd;
+
+/* moments += (sum_r x, sum_r x^2) over obs [rows,width].  Data-parallel ranks all-reduce (SUM) `moments`
+ * and the row count before merging, so that every rank holds the statistics of the global batch. */
+PPK_API int ppk_rms_accumulate(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, void* stream);
+/* RunningMeanStd._update_mean_var_count_from_moments with the batch mean / unbiased variance of the
+ * `batch_rows` rows accumulated in `moments`; clears `moments`. */
+PPK_API int ppk_rms_merge(const PpkRunningMeanStd* rms, double batch_rows, void* stream);
+/* RunningMeanStd.forward in training mode, single rank: accumulate + merge. */
+PPK_API int ppk_rms_update(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, void* stream);
+/* RunningMeanStd.forward output: out = clamp((clamp(obs) - float(mean)) / sqrt(float(var) + eps), -5, 5), fp32. */
+PPK_API int ppk_rms_normalize(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, float* out, void* stream);
+
+typedef enum PpkActivation { PPK_ACT_NONE = 0, PPK_ACT_ELU = 1 } PpkActivation;
+
+/* The first nn.Linear(width -> units) of the actor (and, with `separate: True`, critic) MLP, packed
+ * once at init into fp16 tensor-core operand tiles.  units % 256 == 0; width <= 96. */
+PPK_API size_t ppk_linear_packed_bytes(int32_t units, int32_t width);
+PPK_API int ppk_linear_pack(const float* weight /*[units,width]*/, const float* bias /*[units] or NULL*/, int32_t units,
+                            int32_t width, void* packed, size_t packed_bytes, void* stream);
+/* out[rows,units] fp16 = act(fp16(fp16(norm(obs)) @ fp16(W)^T + fp16(b))): what
+ * `torch.autocast(fp16)` computes for `act(linear(running_mean_std(obs)))` (`mixed_precision: True`,
+ * yaml:50; fp32 accumulation).  `rms` may be NULL (normalize_input False). */
+PPK_API int ppk_policy_first_layer(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, int32_t width,
+                                   const void* packed, int32_t units, int32_t activation, void* out_f16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,14 @@ class PpkBuffers(C.Structure):
     ]
 
 
+class PpkRunningMeanStd(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("width", C.c_int32), ("epsilon", C.c_float), ("clip_obs", C.c_float),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("count", C.c_void_p),
+                ("moments", C.c_void_p)]
+
+
+PPK_ACT_NONE, PPK_ACT_ELU = 0, 1
+
 _LIB = None
 
 
@@ -103,6 +111,22 @@ def load():
         lib.ppk_host_post_physics_step.argtypes = [C.c_void_p, C.POINTER(PpkBuffers), C.c_uint32]
         lib.ppk_host_session_traffic.restype = C.c_int
         lib.ppk_host_session_traffic.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    rp = C.POINTER(PpkRunningMeanStd)
+    lib.ppk_rms_accumulate.restype = C.c_int
+    lib.ppk_rms_accumulate.argtypes = [rp, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.ppk_rms_merge.restype = C.c_int
+    lib.ppk_rms_merge.argtypes = [rp, C.c_double, C.c_void_p]
+    lib.ppk_rms_update.restype = C.c_int
+    lib.ppk_rms_update.argtypes = [rp, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.ppk_rms_normalize.restype = C.c_int
+    lib.ppk_rms_normalize.argtypes = [rp, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.ppk_linear_packed_bytes.restype = C.c_size_t
+    lib.ppk_linear_packed_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.ppk_linear_pack.restype = C.c_int
+    lib.ppk_linear_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.ppk_policy_first_layer.restype = C.c_int
+    lib.ppk_policy_first_layer.argtypes = [rp, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                           C.c_void_p, C.c_void_p]
     if lib.ppk_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libppk.so ABI {lib.ppk_abi_version()} != binding ABI {ABI_VERSION}")
     _LIB = lib

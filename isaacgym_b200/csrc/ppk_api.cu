@@ -8,6 +8,7 @@
 #include "ppk_family.cuh"
 #include "ppk_misc.cuh"
 #include "ppk_adof.cuh"
+#include "ppk_policy.cuh"
 
 using namespace ppk;
 
@@ -321,6 +322,134 @@ PPK_API int ppk_debug_set_trace(unsigned long long* buf) {
   return cudaMemcpyToSymbol(ppk::g_trace, &buf, sizeof(buf)) == cudaSuccess ? PPK_OK : PPK_ERR_CUDA;
 }
 #endif
+
+namespace {
+int rms_args(const PpkRunningMeanStd* r, RmsArgs* a) {
+  if (r == nullptr) return PPK_ERR_NULL;
+  if (r->struct_size != sizeof(PpkRunningMeanStd)) return PPK_ERR_ABI;
+  if (r->width <= 0 || r->width > 1024) return PPK_ERR_SHAPE;
+  if (!r->running_mean || !r->running_var || !r->count) return PPK_ERR_NULL;
+  a->width = r->width; a->eps = r->epsilon; a->clip = r->clip_obs;
+  a->mean = r->running_mean; a->var = r->running_var; a->count = r->count;
+  return PPK_OK;
+}
+}  // namespace
+
+int ppk_rms_accumulate(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, void* stream) {
+  RmsArgs a;
+  int rc = rms_args(rms, &a);
+  if (rc != PPK_OK) return rc;
+  if (rows < 0) return PPK_ERR_SHAPE;
+  if (rows == 0) return PPK_OK;
+  if (!obs || !rms->moments) return PPK_ERR_NULL;
+  const int R = a.width >= 512 ? 1 : 512 / a.width;       // rows per CTA pass
+  long long blocks = (rows + (long long)R * 16 - 1) / ((long long)R * 16);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = sizeof(double) * 2 * R * a.width;
+  rms_moments_kernel<<<(unsigned)blocks, dim3(a.width, R), smem, static_cast<cudaStream_t>(stream)>>>(
+      obs, rows, a.width, a.clip, rms->moments);
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+
+int ppk_rms_merge(const PpkRunningMeanStd* rms, double batch_rows, void* stream) {
+  RmsArgs a;
+  int rc = rms_args(rms, &a);
+  if (rc != PPK_OK) return rc;
+  if (!rms->moments) return PPK_ERR_NULL;
+  if (!(batch_rows > 0.0)) return PPK_ERR_SHAPE;
+  rms_merge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, rms->moments, batch_rows);
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+
+int ppk_rms_update(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, void* stream) {
+  if (rows == 0) return rms ? PPK_OK : PPK_ERR_NULL;
+  int rc = ppk_rms_accumulate(rms, obs, rows, stream);
+  if (rc != PPK_OK) return rc;
+  return ppk_rms_merge(rms, (double)rows, stream);
+}
+
+int ppk_rms_normalize(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, float* out, void* stream) {
+  RmsArgs a;
+  int rc = rms_args(rms, &a);
+  if (rc != PPK_OK) return rc;
+  if (rows < 0) return PPK_ERR_SHAPE;
+  if (rows == 0) return PPK_OK;
+  if (!obs || !out) return PPK_ERR_NULL;
+  long long blocks = (rows * a.width + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  rms_apply_kernel<<<(unsigned)blocks, 256, sizeof(float) * 2 * a.width, static_cast<cudaStream_t>(stream)>>>(a, obs, rows, out);
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+
+size_t ppk_linear_packed_bytes(int32_t units, int32_t width) {
+  if (units <= 0 || width <= 0 || units % kFlN != 0) return 0;
+  return (size_t)units * fl_kpad(width) * sizeof(__half) + (size_t)units * sizeof(float);
+}
+
+int ppk_linear_pack(const float* weight, const float* bias, int32_t units, int32_t width, void* packed, size_t packed_bytes,
+                    void* stream) {
+  if (!weight || !packed) return PPK_ERR_NULL;
+  const size_t need = ppk_linear_packed_bytes(units, width);
+  if (need == 0 || packed_bytes < need) return PPK_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(packed) & 15u) return PPK_ERR_ALIGN;
+  const int kp = fl_kpad(width);
+  __half* ph = static_cast<__half*>(packed);
+  float* pb = reinterpret_cast<float*>(static_cast<unsigned char*>(packed) + (size_t)units * kp * sizeof(__half));
+  linear_pack_kernel<<<148 * 2, 256, 0, static_cast<cudaStream_t>(stream)>>>(weight, bias, units, width, kp, ph, pb);
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+
+extern "C++" {
+namespace {
+template <int KP>
+int launch_first_layer(const FlArgs& k, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(first_layer_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlLayout<KP>::kBytes) !=
+        cudaSuccess) {
+      cudaGetLastError();
+      return PPK_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  const long long units = ((k.rows + kFlM - 1) / kFlM) * (k.units / kFlN);
+  const unsigned grid = (unsigned)(units < 148 ? units : 148);      // persistent: one CTA per SM
+  first_layer_kernel<KP><<<grid, kFlThreads, FlLayout<KP>::kBytes, s>>>(k);
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+}  // namespace
+}  // extern "C++"
+
+int ppk_policy_first_layer(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, int32_t width, const void* packed,
+                           int32_t units, int32_t activation, void* out_f16, void* stream) {
+  FlArgs k;
+  memset(&k, 0, sizeof(k));
+  if (rms != nullptr) {
+    int rc = rms_args(rms, &k.rms);
+    if (rc != PPK_OK) return rc;
+    if (rms->width != width) return PPK_ERR_SHAPE;
+  }
+  if (rows < 0 || width <= 0 || units <= 0 || units % kFlN != 0) return PPK_ERR_SHAPE;
+  if (activation != PPK_ACT_NONE && activation != PPK_ACT_ELU) return PPK_ERR_VARIANT;
+  if (rows == 0) return PPK_OK;
+  if (!obs || !packed || !out_f16) return PPK_ERR_NULL;
+  if ((reinterpret_cast<uintptr_t>(packed) & 15u) || (reinterpret_cast<uintptr_t>(out_f16) & 15u) ||
+      (reinterpret_cast<uintptr_t>(obs) & 3u))
+    return PPK_ERR_ALIGN;
+  const int kp = fl_kpad(width);
+  k.obs = obs; k.rows = rows; k.width = width; k.units = units; k.activation = activation;
+  k.packed = static_cast<const unsigned char*>(packed);
+  k.bias = reinterpret_cast<const float*>(k.packed + (size_t)units * kp * sizeof(__half));
+  k.out = static_cast<__half*>(out_f16);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (kp) {
+    case 32: return launch_first_layer<32>(k, s);
+    case 80: return launch_first_layer<80>(k, s);
+    case 96: return launch_first_layer<96>(k, s);
+    default: return PPK_ERR_SHAPE;     // wider inputs (ADOF: 313) need a K loop over operand stages
+  }
+}
 
 int ppk_stats_reduce(double* stats, double* out, void* stream) {
   if (!stats || !out) return PPK_ERR_NULL;

@@ -1,0 +1,343 @@
+// The learner side of the path: what consumes obs_buf right after the task step.
+//
+//   rl_games `normalize_input: True` (cfg/train/HumanoidPingpongTiltG1PPO.yaml:51) wraps the network input in
+//   RunningMeanStd (rl_games/algos_torch/running_mean_std.py, un-vendored): fp64 running mean / variance /
+//   count, batch moments merged with the parallel-variance formula, y = clamp((x - mean) / sqrt(var + eps), +-5).
+//   The first layer of the MLP (`units: [2048, ...]`, `activation: elu`, yaml:29-30) runs under
+//   `mixed_precision: True` (yaml:50): fp16 operands, fp32 accumulation, fp16 result, ELU on the fp16 tensor.
+//
+// Kernels:
+//   rms_moments_kernel   per-column sum / sum of squares of a batch, fp64, HBM-bound streaming reduction
+//   rms_merge_kernel     batch moments -> running statistics (one CTA)
+//   rms_apply_kernel     stand-alone normalisation, fp32 out
+//   linear_pack_kernel   nn.Linear weight [units, width] fp32 -> fp16 tensor-core operand tiles (once, at init)
+//   first_layer_kernel   obs -> clamp -> normalise -> fp16 -> tcgen05.mma (fp32 accumulators in TMEM)
+//                        -> + bias -> fp16 -> ELU -> fp16 rows, written with bulk stores.  The only GEMM on
+//                        either side of the path; bound by the [rows, units] fp16 write, not by the math.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "ppk_tc.cuh"
+
+namespace ppk {
+
+// ---------------------------------------------------------------------------------------------------
+// running mean / std
+// ---------------------------------------------------------------------------------------------------
+struct RmsArgs {
+  int width;
+  float eps, clip;        // clip <= 0: no observation clamp (VecTask clipObservations, upstream default inf)
+  double* mean;           // [width] running_mean
+  double* var;            // [width] running_var
+  double* count;          // [1]
+};
+
+__device__ __forceinline__ float clamp_obs(float x, float clip) { return clip > 0.0f ? fminf(fmaxf(x, -clip), clip) : x; }
+
+// grid-stride over row blocks; threadIdx.x = column, threadIdx.y = row inside the block of rows.
+// sums[0..W) += sum_r x, sums[W..2W) += sum_r x^2 (fp64 atomics, a few per CTA and column)
+__global__ void rms_moments_kernel(const float* __restrict__ obs, long long rows, int width, float clip, double* sums) {
+  extern __shared__ double red[];            // [2][blockDim.y][width]
+  const int c = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
+  double s = 0.0, ss = 0.0;
+  if (c < width) {
+    for (long long r = (long long)blockIdx.x * R + ry; r < rows; r += (long long)gridDim.x * R) {
+      const float x = clamp_obs(__ldcs(obs + r * width + c), clip);
+      s += (double)x;
+      ss += (double)x * (double)x;
+    }
+    red[ry * width + c] = s;
+    red[(R + ry) * width + c] = ss;
+  }
+  __syncthreads();
+  if (ry == 0 && c < width) {
+    for (int y = 1; y < R; ++y) { s += red[y * width + c]; ss += red[(R + y) * width + c]; }
+    atomicAdd(sums + c, s);
+    atomicAdd(sums + width + c, ss);
+  }
+}
+
+// RunningMeanStd._update_mean_var_count_from_moments with batch mean / unbiased batch variance from
+// the fp64 sums; clears the sums for the next batch.  One CTA.
+__global__ void rms_merge_kernel(RmsArgs a, double* sums, double batch_rows) {
+  const double count = *a.count;
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.width; c += blockDim.x) {
+    const double S = sums[c], SS = sums[a.width + c];
+    const double bmean = S / batch_rows;
+    const double bvar = (SS - S * bmean) / (batch_rows - 1.0);   // torch.var: correction = 1 (nan for one row, as torch)
+    const double delta = bmean - a.mean[c];
+    const double tot = count + batch_rows;
+    const double m2 = a.var[c] * count + bvar * batch_rows + delta * delta * count * batch_rows / tot;
+    a.mean[c] = a.mean[c] + delta * batch_rows / tot;
+    a.var[c] = m2 / tot;
+    sums[c] = 0.0;
+    sums[a.width + c] = 0.0;
+  }
+  if (threadIdx.x == 0) *a.count = count + batch_rows;
+}
+
+// y = clamp((clamp(x) - float(mean)) / sqrt(float(var) + eps), -5, 5), fp32
+__global__ void rms_apply_kernel(RmsArgs a, const float* __restrict__ obs, long long rows, float* __restrict__ out) {
+  extern __shared__ float cst[];      // mean[width], den[width]
+  for (int c = threadIdx.x; c < a.width; c += blockDim.x) {
+    cst[c] = (float)a.mean[c];
+    cst[a.width + c] = sqrtf((float)a.var[c] + a.eps);
+  }
+  __syncthreads();
+  const long long total = rows * a.width;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % a.width);
+    const float x = clamp_obs(__ldcs(obs + e), a.clip);
+    const float y = (x - cst[c]) / cst[a.width + c];
+    __stcs(out + e, fminf(fmaxf(y, -5.0f), 5.0f));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// first layer
+// ---------------------------------------------------------------------------------------------------
+constexpr int kFlM = 128;            // rows per tile = TMEM lanes
+constexpr int kFlN = 256;            // units per chunk = fp32 accumulator columns per buffer
+constexpr int kFlPrepWarps = 2;
+constexpr int kFlEpiWarps = 8;
+constexpr int kFlThreads = 32 * (2 + kFlPrepWarps + kFlEpiWarps);   // producer, mma, prep, epilogue
+constexpr int kFlALbo = kFlM * 16 + 16;   // +16: the prep warps write 16-byte pieces of different K chunks
+constexpr int kFlBLbo = kFlN * 16;
+constexpr int kFlStageRow = (kFlN / 2) * 2 + 16;   // one thread's 128 fp16 outputs + pad (conflict-free 16-byte stores)
+
+__host__ __device__ constexpr int fl_kpad(int width) { return (width + 15) / 16 * 16; }
+__host__ __device__ constexpr size_t fl_chunk_bytes(int kp) { return (size_t)(kp / 8) * kFlBLbo; }
+
+template <int KP>
+struct FlLayout {
+  static constexpr int kKc = KP / 8;
+  static constexpr int kABytes = kKc * kFlALbo;
+  static constexpr int kBBytes = kKc * kFlBLbo;
+  static constexpr int kOffB = 2 * kABytes;
+  static constexpr int kOffStage = kOffB + 2 * kBBytes;
+  static constexpr int kOffCst = kOffStage + 32 * kFlEpiWarps * kFlStageRow;
+  static constexpr int kOffBar = kOffCst + 2 * KP * 4;
+  static constexpr int kBytes = kOffBar + 12 * 8 + 16;
+  static_assert(kOffB % 16 == 0 && kOffStage % 16 == 0 && kOffCst % 16 == 0 && kOffBar % 8 == 0, "alignment");
+  static_assert(kBytes <= 227 * 1024, "shared memory budget");
+};
+
+// packed weight blob: [units/256 chunks][KP/8][256][8] fp16, then bias [units] as fp32 values of the fp16-rounded bias
+__global__ void linear_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias, int units, int width, int kp,
+                                   __half* __restrict__ packed, float* __restrict__ bias_out) {
+  const long long total = (long long)units * kp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // i enumerates the packed order
+    const int j = (int)(i & 7);
+    const long long t = i >> 3;
+    const int nl = (int)(t % kFlN);
+    const long long t2 = t / kFlN;
+    const int kc = (int)(t2 % (kp / 8));
+    const int chunk = (int)(t2 / (kp / 8));
+    const int n = chunk * kFlN + nl, k = kc * 8 + j;
+    packed[i] = __float2half_rn(k < width ? w[(size_t)n * width + k] : 0.0f);
+  }
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < units; n += gridDim.x * blockDim.x)
+    bias_out[n] = bias ? __half2float(__float2half_rn(bias[n])) : 0.0f;
+}
+
+struct FlArgs {
+  const float* obs;          // [rows, width]
+  long long rows;
+  int width, units, activation;   // activation: 0 none, 1 ELU
+  RmsArgs rms;               // rms.mean == nullptr: no normalisation
+  const unsigned char* packed;
+  const float* bias;         // inside the packed blob
+  __half* out;               // [rows, units]
+};
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int KP>
+__global__ void __launch_bounds__(kFlThreads, 1) first_layer_kernel(const __grid_constant__ FlArgs k) {
+  using L = FlLayout<KP>;
+  extern __shared__ __align__(128) unsigned char fl_smem[];
+  unsigned char* a_s = fl_smem;
+  unsigned char* b_s = fl_smem + L::kOffB;
+  unsigned char* stage_s = fl_smem + L::kOffStage;
+  float* cst = reinterpret_cast<float*>(fl_smem + L::kOffCst);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fl_smem + L::kOffBar);
+  uint64_t *b_full = bars, *b_empty = bars + 2, *a_full = bars + 4, *a_empty = bars + 6, *acc_full = bars + 8,
+           *acc_empty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NC = k.units / kFlN;
+  const long long MT = (k.rows + kFlM - 1) / kFlM;
+  const long long U = MT * NC;
+  const long long u_begin = U * blockIdx.x / gridDim.x, u_end = U * (blockIdx.x + 1) / gridDim.x;
+  const long long mt_begin = u_begin / NC;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1);
+      mbar_init(a_full + i, 32 * kFlPrepWarps); mbar_init(a_empty + i, 1);
+      mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 32 * kFlEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
+  // normalisation constants: float(mean), sqrt(float(var) + eps)
+  for (int c = threadIdx.x; c < KP; c += kFlThreads) {
+    const bool on = k.rms.mean != nullptr && c < k.width;
+    cst[c] = on ? (float)k.rms.mean[c] : 0.0f;
+    cst[KP + c] = on ? sqrtf((float)k.rms.var[c] + k.rms.eps) : 1.0f;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== weight-chunk producer: one bulk copy per unit into the 2-deep ring =====
+    if (lane == 0) {
+      for (long long u = u_begin; u < u_end; ++u) {
+        const long long it = u - u_begin;
+        const int s = (int)(it & 1), ph = (int)((it >> 1) & 1);
+        const int nc = (int)(u % NC);
+        mbar_wait(b_empty + s, ph ^ 1);
+        mbar_arrive_expect_tx(b_full + s, (uint32_t)L::kBBytes);
+        bulk_g2s(b_s + s * L::kBBytes, k.packed + (size_t)nc * L::kBBytes, (uint32_t)L::kBBytes, b_full + s);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: a single thread =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::instr_desc_f16_f32(kFlM, kFlN);
+      for (long long u = u_begin; u < u_end; ++u) {
+        const long long it = u - u_begin;
+        const int s = (int)(it & 1), ph = (int)((it >> 1) & 1);
+        const long long mt = u / NC;
+        const int nc = (int)(u - mt * NC);
+        const long long j = mt - mt_begin;
+        const int ab = (int)(j & 1), aph = (int)((j >> 1) & 1);
+        if (it == 0 || nc == 0) mbar_wait(a_full + ab, aph);
+        mbar_wait(b_full + s, ph);
+        mbar_wait(acc_empty + s, ph ^ 1);
+        tc::fence_after_sync();
+        const uint32_t a0 = smem_u32(a_s + ab * L::kABytes), b0 = smem_u32(b_s + s * L::kBBytes);
+#pragma unroll
+        for (int kk = 0; kk < KP / 16; ++kk)
+          tc::mma_f16(tmem_base + s * kFlN, tc::smem_desc(a0 + kk * 2 * kFlALbo, kFlALbo, 128),
+                      tc::smem_desc(b0 + kk * 2 * kFlBLbo, kFlBLbo, 128), idesc, kk > 0);
+        tc::mma_commit(b_empty + s);
+        if (u == u_end - 1 || nc == NC - 1) tc::mma_commit(a_empty + ab);
+        tc::mma_commit(acc_full + s);
+      }
+    }
+  } else if (warp < 2 + kFlPrepWarps) {
+    // ===== row-tile preparation: clamp, normalise, fp16, tensor-core operand layout =====
+    const int t = threadIdx.x - 64;
+    const long long mt_last = (u_end - 1) / NC;
+    const bool vec = (k.width % 4 == 0) && ((reinterpret_cast<uintptr_t>(k.obs) & 15u) == 0);
+    for (long long mt = mt_begin; mt <= mt_last && u_begin < u_end; ++mt) {
+      const long long j = mt - mt_begin;
+      const int ab = (int)(j & 1), aph = (int)((j >> 1) & 1);
+      mbar_wait(a_empty + ab, aph ^ 1);
+      unsigned char* dst = a_s + ab * L::kABytes;
+      for (int item = t; item < kFlM * L::kKc; item += 32 * kFlPrepWarps) {
+        const int r = item / L::kKc, kc = item - r * L::kKc;
+        const long long row = mt * kFlM + r;
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = 0.0f;
+        if (row < k.rows) {
+          const float* src = k.obs + row * k.width + kc * 8;
+          if (vec) {
+            if (kc * 8 < k.width) { float4 v = __ldcs(reinterpret_cast<const float4*>(src)); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+            if (kc * 8 + 4 < k.width) { float4 v = __ldcs(reinterpret_cast<const float4*>(src) + 1); x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (kc * 8 + i < k.width) x[i] = __ldcs(src + i);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = kc * 8 + i;
+            float y = clamp_obs(x[i], k.rms.clip);
+            if (k.rms.mean != nullptr) y = fminf(fmaxf((y - cst[c]) / cst[KP + c], -5.0f), 5.0f);
+            x[i] = (c < k.width) ? y : 0.0f;
+          }
+        }
+        uint4 pk;
+        pk.x = pack_half2(x[0], x[1]); pk.y = pack_half2(x[2], x[3]); pk.z = pack_half2(x[4], x[5]); pk.w = pack_half2(x[6], x[7]);
+        *reinterpret_cast<uint4*>(dst + kc * kFlALbo + r * 16) = pk;
+      }
+      tc::fence_proxy_async_smem();
+      tc::mbar_arrive(a_full + ab);
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> + bias -> fp16 -> activation -> fp16 row piece -> bulk store =====
+    const int ew = warp - (2 + kFlPrepWarps);
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int h = ew >> 2;                  // column half of the chunk
+    const int r_local = q * 32 + lane;
+    unsigned char* my_stage = stage_s + (size_t)(ew * 32 + lane) * kFlStageRow;
+    for (long long u = u_begin; u < u_end; ++u) {
+      const long long it = u - u_begin;
+      const int s = (int)(it & 1), ph = (int)((it >> 1) & 1);
+      const long long mt = u / NC;
+      const int nc = (int)(u - mt * NC);
+      const long long row = mt * kFlM + r_local;
+      const int col0 = nc * kFlN + h * (kFlN / 2);
+      mbar_wait(acc_full + s, ph);
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kFlN + h * (kFlN / 2));
+      tc::bulk_wait_read0();                // the previous row piece has left shared memory
+#pragma unroll 1
+      for (int g = 0; g < (kFlN / 2) / 32; ++g) {
+        uint32_t v[32];
+        tc::tmem_ld32(taddr + g * 32, v);
+        tc::tmem_ld_wait();
+        if (g == (kFlN / 2) / 32 - 1) {     // accumulator drained: the next MMA into this buffer may start
+          tc::fence_before_sync();
+          tc::mbar_arrive(acc_empty + s);
+        }
+        const float4* b4 = reinterpret_cast<const float4*>(k.bias + col0 + g * 32);
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = __ldg(b4 + i);
+          float f[4] = {__uint_as_float(v[4 * i]) + b.x, __uint_as_float(v[4 * i + 1]) + b.y,
+                        __uint_as_float(v[4 * i + 2]) + b.z, __uint_as_float(v[4 * i + 3]) + b.w};
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            __half2 lin = __floats2half2_rn(f[2 * p], f[2 * p + 1]);     // the fp16 output of the linear layer
+            if (k.activation == 1) {
+              const float2 xf = __half22float2(lin);
+              const float e0 = xf.x > 0.0f ? xf.x : __expf(xf.x) - 1.0f;
+              const float e1 = xf.y > 0.0f ? xf.y : __expf(xf.y) - 1.0f;
+              lin = __floats2half2_rn(e0, e1);
+            }
+            o[2 * i + p] = *reinterpret_cast<uint32_t*>(&lin);
+          }
+        }
+        uint4* sp = reinterpret_cast<uint4*>(my_stage + g * 64);
+        sp[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        sp[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        sp[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        sp[3] = make_uint4(o[12], o[13], o[14], o[15]);
+      }
+      tc::fence_proxy_async_smem();
+      if (row < k.rows) tc::bulk_s2g(k.out + (size_t)row * k.units + col0, my_stage, (kFlN / 2) * 2);
+      tc::bulk_commit();
+    }
+    tc::bulk_wait_all();
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace ppk

@@ -44,11 +44,11 @@ def test_abi_version_and_strerror(lib):
 
 def test_struct_sizes_match_the_header(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "ppk.h"\nint main(){printf("%zu %zu\\n", sizeof(PpkTask), sizeof(PpkBuffers));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "ppk.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(PpkTask), sizeof(PpkBuffers), sizeof(PpkRunningMeanStd));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
-    a, b = map(int, subprocess.check_output([str(exe)]).split())
-    assert a == C.sizeof(N.PpkTask) and b == C.sizeof(N.PpkBuffers)
+    a, b, c = map(int, subprocess.check_output([str(exe)]).split())
+    assert a == C.sizeof(N.PpkTask) and b == C.sizeof(N.PpkBuffers) and c == C.sizeof(N.PpkRunningMeanStd)
 
 
 def test_argument_validation_returns_error_codes(lib):
@@ -98,3 +98,20 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_learner_side_argument_validation(lib):
+    assert lib.ppk_linear_packed_bytes(2048, 80) == 2048 * 80 * 2 + 2048 * 4
+    assert lib.ppk_linear_packed_bytes(2048, 94) == 2048 * 96 * 2 + 2048 * 4      # K padded to a multiple of 16
+    assert lib.ppk_linear_packed_bytes(1000, 80) == 0                             # units % 256 != 0
+    rms = N.PpkRunningMeanStd()
+    rms.struct_size = C.sizeof(N.PpkRunningMeanStd)
+    rms.width = 80
+    assert lib.ppk_rms_update(rms, 0x1000, 16, None) == -1                        # NULL statistics
+    rms.struct_size = 8
+    assert lib.ppk_rms_normalize(rms, 0x1000, 16, 0x1000, None) == -6             # PPK_ERR_ABI
+    assert lib.ppk_policy_first_layer(None, 0x1000, 16, 80, 0x1000, 1000, 1, 0x1000, None) == -2   # units
+    assert lib.ppk_policy_first_layer(None, 0x1000, 16, 313, 0x1000, 2048, 1, 0x1000, None) == -2  # width > 96
+    assert lib.ppk_policy_first_layer(None, 0x1000, 16, 80, 0x1000, 2048, 7, 0x1000, None) == -4   # activation
+    assert lib.ppk_policy_first_layer(None, None, 16, 80, 0x1000, 2048, 1, 0x1000, None) == -1
+    assert lib.ppk_policy_first_layer(None, 0x1000, 0, 80, 0x1000, 2048, 1, 0x1000, None) == 0     # empty batch

@@ -1,0 +1,114 @@
+"""GPU parity of the learner-side consumers of obs_buf through the C ABI:
+RunningMeanStd (fp64 statistics, fp32 output) and the fused normalise + first MLP layer (tcgen05, fp16).
+Tolerances: running_mean / running_var rtol 1e-6 (fp64 sums on the device vs torch's fp32 batch moments
+promoted to fp64); normalised obs bit-exact given the same statistics; first layer: identical up to the
+fp32 summation order inside the dot product -> at most ONE fp16 ulp of the linear output (+2e-5 absolute
+where the terms cancel; two ulps after ELU, see assert_fp16_close), on a small fraction of the entries."""
+import pytest
+import torch
+
+from isaacgym_b200.policy_input import FirstLayer, RunningMeanStd
+from oracle import policy_oracle as P
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def batch(rows, width, seed, scale=2.0, shift=0.7):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(rows, width, generator=g) * scale + shift
+
+
+@pytest.mark.parametrize("width", [80, 94, 313, 24])
+def test_running_mean_std_matches_restatement(width):
+    ours = RunningMeanStd(width, device=DEV)
+    ref = P.RunningMeanStd(width)
+    for i, rows in enumerate((4096, 1000, 33)):
+        x = batch(rows, width, 10 + i)
+        y = ours.forward(x.to(DEV))
+        want = ref.forward(x)
+        torch.testing.assert_close(ours.running_mean.cpu(), ref.running_mean, rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(ours.running_var.cpu(), ref.running_var, rtol=1e-6, atol=1e-7)
+        assert float(ours.count) == float(ref.count)
+        torch.testing.assert_close(y.cpu(), want, rtol=1e-5, atol=1e-6)
+    # frozen statistics (rollout / eval mode): the output is bit-exact given the same fp64 state
+    ours.eval()
+    ref.training = False
+    ref.running_mean, ref.running_var = ours.running_mean.cpu(), ours.running_var.cpu()
+    x = batch(2048, width, 99)
+    assert torch.equal(ours(x.to(DEV)).cpu(), ref.forward(x))
+    assert float(ours.count) == float(ref.count)          # eval mode does not update
+
+
+def test_observation_clamp_feeds_the_statistics():
+    ours = RunningMeanStd(80, clip_obs=1.5, device=DEV)
+    ref = P.RunningMeanStd(80)
+    x = batch(3000, 80, 4, scale=3.0)
+    y = ours.forward(x.to(DEV))
+    want = ref.forward(P.clip_observations(x, 1.5))
+    torch.testing.assert_close(ours.running_var.cpu(), ref.running_var, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(y.cpu(), want, rtol=1e-5, atol=1e-6)
+
+
+def assert_fp16_close(got, want, ctx, ulps=1):
+    g, w = got.float().cpu(), want.float()
+    # one fp16 ulp, plus the fp32 summation-order noise of an 80..96-term dot product whose terms are O(1)
+    # (it dominates when the terms cancel to a result near zero, where an fp16 ulp is tiny)
+    # ELU: a one-ulp flip of the fp16 pre-activation x in (-0.69, -0.5) moves exp(x)-1, which has a finer
+    # ulp than x, by up to two of ITS ulps -> ulps=2 for activated outputs
+    bad = (g - w).abs() > ulps * 2.0 ** -10 * w.abs() + 2e-5
+    assert int(bad.sum()) == 0, f"{ctx}: {int(bad.sum())} of {bad.numel()} entries off by more than one fp16 ulp; " \
+                                f"max abs err {float((g - w).abs().max())}"
+    assert float((g != w).float().mean()) < 0.02, f"{ctx}: too many entries differ in the last bit"
+
+
+@pytest.mark.parametrize("rows,width,units", [(4096, 80, 2048), (1000, 80, 512), (129, 94, 256), (5, 24, 256),
+                                              (20000, 80, 4096)])
+@pytest.mark.parametrize("act", ["elu", "None"])
+def test_first_layer_matches_autocast_restatement(rows, width, units, act):
+    g = torch.Generator().manual_seed(rows + width)
+    x = batch(rows, width, rows)
+    w = torch.randn(units, width, generator=g) / width ** 0.5
+    b = torch.randn(units, generator=g) * 0.1
+    rms_ref = P.RunningMeanStd(width)
+    rms_ref.update(batch(5000, width, 1))
+    rms = RunningMeanStd(width, device=DEV).eval()
+    rms.running_mean.copy_(rms_ref.running_mean)
+    rms.running_var.copy_(rms_ref.running_var)
+    layer = FirstLayer(w.to(DEV), b.to(DEV), activation=act, running_mean_std=rms)
+    got = layer(x.to(DEV))
+    torch.cuda.synchronize()
+    want = P.first_layer(rms_ref.normalize(x), w, b, act)
+    assert got.dtype == torch.float16 and tuple(got.shape) == (rows, units)
+    assert_fp16_close(got, want, f"rows={rows} width={width} units={units} act={act}", ulps=2 if act == "elu" else 1)
+
+
+def test_first_layer_without_normalisation_and_without_bias():
+    g = torch.Generator().manual_seed(8)
+    x = batch(777, 80, 8, scale=1.0, shift=0.0)
+    w = torch.randn(256, 80, generator=g) / 80 ** 0.5
+    layer = FirstLayer(w.to(DEV), None, activation="elu", running_mean_std=None)
+    got = layer(x.to(DEV))
+    assert_fp16_close(got, P.first_layer(x, w, None, "elu"), "no rms, no bias", ulps=2)
+
+
+def test_first_layer_consumes_the_task_step_output():
+    """obs_buf straight out of the fused task step -> normalise -> first layer, both sides of the path."""
+    from isaacgym_b200.config import CONFIGS
+    from isaacgym_b200.synth import make_state
+    from isaacgym_b200.tasks import make_task
+    cfg = CONFIGS["tilt"]
+    st = make_state(cfg, 4096, seed=12, adversarial=False)
+    task = make_task("tilt", st, device=DEV)
+    task.post_physics_step()
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(2048, 80, generator=g) / 80 ** 0.5
+    b = torch.zeros(2048)
+    rms = RunningMeanStd(80, device=DEV)
+    rms.update(task.obs_buf)
+    rms.eval()
+    got = FirstLayer(w.to(DEV), b.to(DEV), "elu", rms)(task.obs_buf)
+    ref = P.RunningMeanStd(80)
+    ref.running_mean, ref.running_var = rms.running_mean.cpu(), rms.running_var.cpu()
+    want = P.first_layer(ref.normalize(task.obs_buf.cpu()), w, b, "elu")
+    assert_fp16_close(got, want, "task step -> first layer", ulps=2)

@@ -148,3 +148,50 @@ def test_unnormalised_quaternion_is_not_normalised():
     q = _rand_unit_quat(10, seed=4)
     v = torch.randn(10, 3, generator=torch.Generator().manual_seed(5))
     assert not torch.allclose(J.my_quat_rotate(2 * q, v), J.my_quat_rotate(q, v))
+
+
+# ---- learner side ----------------------------------------------------------------
+def test_running_mean_std_restatement_properties():
+    """rl_games is absent (parity unpinned): check the restated update against first principles -- merging
+    batches one by one equals the statistics of their concatenation plus the one prior pseudo-sample
+    (mean 0, var 1, count 1) the module starts from."""
+    from oracle import policy_oracle as P
+    g = torch.Generator().manual_seed(3)
+    rms = P.RunningMeanStd(7)
+    batches = [torch.randn(n, 7, generator=g, dtype=torch.float32) * 3 + 1.5 for n in (64, 257, 1000)]
+    for b in batches:
+        rms.forward(b)
+    allx = torch.cat(batches).double()
+    n = allx.shape[0]
+    mean = allx.mean(0)
+    m2 = ((allx - mean) ** 2).sum(0)                       # n-weighted second moment about the data mean
+    tot = n + 1.0
+    want_mean = mean * n / tot                             # merged with the prior sample at 0
+    # chained parallel-variance merges with unbiased batch variances are not the plain pooled variance; replay
+    # them in float64 with the same formula on exact batch moments instead
+    m, v, c = torch.zeros(7, dtype=torch.float64), torch.ones(7, dtype=torch.float64), 1.0
+    for b in batches:
+        bd = b.double()
+        m, v, c = P.RunningMeanStd._update_mean_var_count_from_moments(m, v, c, bd.mean(0), bd.var(0), bd.shape[0])
+    torch.testing.assert_close(rms.running_mean, want_mean, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(rms.running_mean, m, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(rms.running_var, v, rtol=1e-5, atol=1e-6)
+    assert float(rms.count) == tot and m2.min() > 0
+    y = rms.normalize(batches[0])
+    assert float(y.abs().max()) <= 5.0 and y.dtype == torch.float32
+
+
+def test_first_layer_restatement_equals_torch_autocast():
+    """The fp16 first layer restated with explicit roundings is what torch.autocast(float16) computes."""
+    from oracle import policy_oracle as P
+    g = torch.Generator().manual_seed(5)
+    for width, units in ((80, 2048), (94, 512), (24, 256)):
+        x = (torch.randn(300, width, generator=g) * 2).clamp(-5, 5)
+        w = torch.randn(units, width, generator=g) / width ** 0.5
+        b = torch.randn(units, generator=g) * 0.1
+        for act in ("elu", "None"):
+            a = P.first_layer(x, w, b, act).float()
+            t = P.first_layer_torch_autocast(x, w, b, act).float()
+            # identical up to fp32 summation order: at most one fp16 ulp, on a small fraction of entries
+            assert float(((a - t).abs() > 2.0 ** -10 * t.abs() + 1e-7).float().mean()) == 0.0
+            assert float((a != t).float().mean()) < 0.01
