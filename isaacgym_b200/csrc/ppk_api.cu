@@ -406,8 +406,10 @@ template <int KP>
 int launch_first_layer(const FlArgs& k, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(first_layer_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlLayout<KP>::kBytes) !=
-        cudaSuccess) {
+    if (cudaFuncSetAttribute(first_layer_kernel<KP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlLayout<KP>::kBytes) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(first_layer_kernel<KP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlLayout<KP>::kBytes) !=
+            cudaSuccess) {
       cudaGetLastError();
       return PPK_ERR_LAUNCH;
     }
@@ -415,7 +417,8 @@ int launch_first_layer(const FlArgs& k, cudaStream_t s) {
   }
   const long long units = ((k.rows + kFlM - 1) / kFlM) * (k.units / kFlN);
   const unsigned grid = (unsigned)(units < 148 ? units : 148);      // persistent: one CTA per SM
-  first_layer_kernel<KP><<<grid, kFlThreads, FlLayout<KP>::kBytes, s>>>(k);
+  if (k.activation == PPK_ACT_ELU) first_layer_kernel<KP, 1><<<grid, kFlThreads, FlLayout<KP>::kBytes, s>>>(k);
+  else first_layer_kernel<KP, 0><<<grid, kFlThreads, FlLayout<KP>::kBytes, s>>>(k);
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 }  // namespace

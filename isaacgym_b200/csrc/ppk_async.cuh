@@ -42,6 +42,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
+// for waits that are long by design (a producer far ahead of its consumer): back off between polls so
+// the spinning warp does not compete for issue slots with the warps doing the work
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  uint32_t spins = 0;
+  for (;;) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 24)) __trap();
+    __nanosleep(200);
+  }
+}
+
 // one lane of the (fully converged) warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

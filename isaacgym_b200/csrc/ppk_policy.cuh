@@ -97,14 +97,18 @@ __global__ void rms_apply_kernel(RmsArgs a, const float* __restrict__ obs, long 
 // ---------------------------------------------------------------------------------------------------
 // first layer
 // ---------------------------------------------------------------------------------------------------
+#ifndef PPK_FL_DBG
+#define PPK_FL_DBG 0        // A/B builds only: 1 no epilogue math, 2 no global stores, 4 no MMA, 8 no prep loads, 16 no weight loads
+#endif
 constexpr int kFlM = 128;            // rows per tile = TMEM lanes
 constexpr int kFlN = 256;            // units per chunk = fp32 accumulator columns per buffer
-constexpr int kFlPrepWarps = 2;
-constexpr int kFlEpiWarps = 8;
+constexpr int kFlPrepWarps = 4;
+constexpr int kFlEpiWarps = 16;          // four per TMEM lane quarter: the epilogue is latency-bound per warp
+constexpr int kFlEpiCols = kFlN / (kFlEpiWarps / 4);   // accumulator columns per epilogue warp and unit
 constexpr int kFlThreads = 32 * (2 + kFlPrepWarps + kFlEpiWarps);   // producer, mma, prep, epilogue
 constexpr int kFlALbo = kFlM * 16 + 16;   // +16: the prep warps write 16-byte pieces of different K chunks
 constexpr int kFlBLbo = kFlN * 16;
-constexpr int kFlStageRow = (kFlN / 2) * 2 + 16;   // one thread's 128 fp16 outputs + pad (conflict-free 16-byte stores)
+constexpr int kFlStageRow = kFlEpiCols * 2 + 16;   // one thread's fp16 outputs of a unit + pad (conflict-free 16-byte stores)
 
 __host__ __device__ constexpr int fl_kpad(int width) { return (width + 15) / 16 * 16; }
 __host__ __device__ constexpr size_t fl_chunk_bytes(int kp) { return (size_t)(kp / 8) * kFlBLbo; }
@@ -152,12 +156,20 @@ struct FlArgs {
   __half* out;               // [rows, units]
 };
 
+// 2^x, one MUFU (the non-ftz form costs two more multiplies and a compare per element for denormal
+// results, which the following "- 1" discards anyway)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int KP>
+template <int KP, int ACT>
 __global__ void __launch_bounds__(kFlThreads, 1) first_layer_kernel(const __grid_constant__ FlArgs k) {
   using L = FlLayout<KP>;
   extern __shared__ __align__(128) unsigned char fl_smem[];
@@ -204,7 +216,8 @@ __global__ void __launch_bounds__(kFlThreads, 1) first_layer_kernel(const __grid
         const long long it = u - u_begin;
         const int s = (int)(it & 1), ph = (int)((it >> 1) & 1);
         const int nc = (int)(u % NC);
-        mbar_wait(b_empty + s, ph ^ 1);
+        mbar_wait_relaxed(b_empty + s, ph ^ 1);
+        if (PPK_FL_DBG & 16) { tc::mbar_arrive(b_full + s); continue; }
         mbar_arrive_expect_tx(b_full + s, (uint32_t)L::kBBytes);
         bulk_g2s(b_s + s * L::kBBytes, k.packed + (size_t)nc * L::kBBytes, (uint32_t)L::kBBytes, b_full + s);
       }
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(kFlThreads, 1) first_layer_kernel(const __grid
         tc::fence_after_sync();
         const uint32_t a0 = smem_u32(a_s + ab * L::kABytes), b0 = smem_u32(b_s + s * L::kBBytes);
 #pragma unroll
-        for (int kk = 0; kk < KP / 16; ++kk)
+        for (int kk = 0; kk < ((PPK_FL_DBG & 4) ? 0 : KP / 16); ++kk)
           tc::mma_f16(tmem_base + s * kFlN, tc::smem_desc(a0 + kk * 2 * kFlALbo, kFlALbo, 128),
                       tc::smem_desc(b0 + kk * 2 * kFlBLbo, kFlBLbo, 128), idesc, kk > 0);
         tc::mma_commit(b_empty + s);
@@ -236,41 +249,55 @@ __global__ void __launch_bounds__(kFlThreads, 1) first_layer_kernel(const __grid
     }
   } else if (warp < 2 + kFlPrepWarps) {
     // ===== row-tile preparation: clamp, normalise, fp16, tensor-core operand layout =====
-    const int t = threadIdx.x - 64;
+    const int t = threadIdx.x - 64;     // warps 2..5
     const long long mt_last = (u_end - 1) / NC;
     const bool vec = (k.width % 4 == 0) && ((reinterpret_cast<uintptr_t>(k.obs) & 15u) == 0);
     for (long long mt = mt_begin; mt <= mt_last && u_begin < u_end; ++mt) {
       const long long j = mt - mt_begin;
       const int ab = (int)(j & 1), aph = (int)((j >> 1) & 1);
-      mbar_wait(a_empty + ab, aph ^ 1);
+      mbar_wait_relaxed(a_empty + ab, aph ^ 1);
       unsigned char* dst = a_s + ab * L::kABytes;
-      for (int item = t; item < kFlM * L::kKc; item += 32 * kFlPrepWarps) {
-        const int r = item / L::kKc, kc = item - r * L::kKc;
-        const long long row = mt * kFlM + r;
-        float x[8];
+      constexpr int kItems = kFlM * L::kKc, kStride = 32 * kFlPrepWarps, kBatch = 5;
+      for (int base = t; base < kItems; base += kStride * kBatch) {
+        float x[kBatch][8];
+        // all loads of the batch first (independent, in flight together), then the arithmetic
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = 0.0f;
-        if (row < k.rows) {
-          const float* src = k.obs + row * k.width + kc * 8;
-          if (vec) {
-            if (kc * 8 < k.width) { float4 v = __ldcs(reinterpret_cast<const float4*>(src)); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
-            if (kc * 8 + 4 < k.width) { float4 v = __ldcs(reinterpret_cast<const float4*>(src) + 1); x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w; }
-          } else {
+        for (int bi = 0; bi < kBatch; ++bi) {
+          const int item = base + bi * kStride;
+          const int r = item / L::kKc, kc = item - r * L::kKc;
+          const long long row = mt * kFlM + r;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (kc * 8 + i < k.width) x[i] = __ldcs(src + i);
+          for (int i = 0; i < 8; ++i) x[bi][i] = 0.0f;
+          if (item < kItems && row < k.rows && !(PPK_FL_DBG & 8)) {
+            const float* src = k.obs + row * k.width + kc * 8;
+            if (vec) {
+              if (kc * 8 < k.width) { float4 v = __ldcs(reinterpret_cast<const float4*>(src)); x[bi][0] = v.x; x[bi][1] = v.y; x[bi][2] = v.z; x[bi][3] = v.w; }
+              if (kc * 8 + 4 < k.width) { float4 v = __ldcs(reinterpret_cast<const float4*>(src) + 1); x[bi][4] = v.x; x[bi][5] = v.y; x[bi][6] = v.z; x[bi][7] = v.w; }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (kc * 8 + i < k.width) x[bi][i] = __ldcs(src + i);
+            }
           }
+        }
+#pragma unroll
+        for (int bi = 0; bi < kBatch; ++bi) {
+          const int item = base + bi * kStride;
+          if (item >= kItems) break;
+          const int r = item / L::kKc, kc = item - r * L::kKc;
+          const bool live = mt * kFlM + r < k.rows;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int c = kc * 8 + i;
-            float y = clamp_obs(x[i], k.rms.clip);
+            float y = clamp_obs(x[bi][i], k.rms.clip);
             if (k.rms.mean != nullptr) y = fminf(fmaxf((y - cst[c]) / cst[KP + c], -5.0f), 5.0f);
-            x[i] = (c < k.width) ? y : 0.0f;
+            x[bi][i] = (live && c < k.width) ? y : 0.0f;
           }
+          uint4 pk;
+          pk.x = pack_half2(x[bi][0], x[bi][1]); pk.y = pack_half2(x[bi][2], x[bi][3]);
+          pk.z = pack_half2(x[bi][4], x[bi][5]); pk.w = pack_half2(x[bi][6], x[bi][7]);
+          *reinterpret_cast<uint4*>(dst + kc * kFlALbo + r * 16) = pk;
         }
-        uint4 pk;
-        pk.x = pack_half2(x[0], x[1]); pk.y = pack_half2(x[2], x[3]); pk.z = pack_half2(x[4], x[5]); pk.w = pack_half2(x[6], x[7]);
-        *reinterpret_cast<uint4*>(dst + kc * kFlALbo + r * 16) = pk;
       }
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(a_full + ab);
@@ -279,26 +306,23 @@ __global__ void __launch_bounds__(kFlThreads, 1) first_layer_kernel(const __grid
     // ===== epilogue: TMEM -> registers -> + bias -> fp16 -> activation -> fp16 row piece -> bulk store =====
     const int ew = warp - (2 + kFlPrepWarps);
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int h = ew >> 2;                  // column half of the chunk
-    const int r_local = q * 32 + lane;
+    const int cq = ew >> 2;                 // which kFlEpiCols-wide slice of the chunk
     unsigned char* my_stage = stage_s + (size_t)(ew * 32 + lane) * kFlStageRow;
     for (long long u = u_begin; u < u_end; ++u) {
       const long long it = u - u_begin;
       const int s = (int)(it & 1), ph = (int)((it >> 1) & 1);
       const long long mt = u / NC;
       const int nc = (int)(u - mt * NC);
-      const long long row = mt * kFlM + r_local;
-      const int col0 = nc * kFlN + h * (kFlN / 2);
+      const int col0 = nc * kFlN + cq * kFlEpiCols;
       mbar_wait(acc_full + s, ph);
       tc::fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kFlN + h * (kFlN / 2));
-      tc::bulk_wait_read0();                // the previous row piece has left shared memory
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kFlN + cq * kFlEpiCols);
 #pragma unroll 1
-      for (int g = 0; g < (kFlN / 2) / 32; ++g) {
+      for (int g = 0; g < kFlEpiCols / 32; ++g) {
         uint32_t v[32];
         tc::tmem_ld32(taddr + g * 32, v);
         tc::tmem_ld_wait();
-        if (g == (kFlN / 2) / 32 - 1) {     // accumulator drained: the next MMA into this buffer may start
+        if (g == kFlEpiCols / 32 - 1) {     // accumulator drained: the next MMA into this buffer may start
           tc::fence_before_sync();
           tc::mbar_arrive(acc_empty + s);
         }
@@ -312,10 +336,10 @@ __global__ void __launch_bounds__(kFlThreads, 1) first_layer_kernel(const __grid
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
             __half2 lin = __floats2half2_rn(f[2 * p], f[2 * p + 1]);     // the fp16 output of the linear layer
-            if (k.activation == 1) {
+            if (ACT == 1 && !(PPK_FL_DBG & 1)) {
               const float2 xf = __half22float2(lin);
-              const float e0 = xf.x > 0.0f ? xf.x : __expf(xf.x) - 1.0f;
-              const float e1 = xf.y > 0.0f ? xf.y : __expf(xf.y) - 1.0f;
+              const float e0 = xf.x > 0.0f ? xf.x : ex2_ftz(xf.x * 1.4426950408889634f) - 1.0f;
+              const float e1 = xf.y > 0.0f ? xf.y : ex2_ftz(xf.y * 1.4426950408889634f) - 1.0f;
               lin = __floats2half2_rn(e0, e1);
             }
             o[2 * i + p] = *reinterpret_cast<uint32_t*>(&lin);
@@ -327,11 +351,25 @@ __global__ void __launch_bounds__(kFlThreads, 1) first_layer_kernel(const __grid
         sp[2] = make_uint4(o[8], o[9], o[10], o[11]);
         sp[3] = make_uint4(o[12], o[13], o[14], o[15]);
       }
-      tc::fence_proxy_async_smem();
-      if (row < k.rows) tc::bulk_s2g(k.out + (size_t)row * k.units + col0, my_stage, (kFlN / 2) * 2);
-      tc::bulk_commit();
+      // the warp's 32 row pieces go out coalesced: per instruction kRowsPer rows, kPieces lanes x 16 B each.
+      // (One bulk store per row was tried first: the copy engine serves ~1 operation per 46 cycles per SM,
+      // 256 of them per unit cost 4x the whole HBM budget.)
+      __syncwarp();
+      const unsigned char* wstage = stage_s + (size_t)(ew * 32) * kFlStageRow;
+      constexpr int kPieces = kFlEpiCols * 2 / 16, kRowsPer = 32 / kPieces;
+      const long long row_w = mt * kFlM + q * 32;
+      const int rr0 = lane / kPieces, piece = lane % kPieces;
+      const int live = (int)min((long long)32, k.rows - row_w);       // rows of this warp that exist
+      uint4* gdst = reinterpret_cast<uint4*>(k.out + (size_t)(row_w + rr0) * k.units + col0) + piece;
+      const unsigned char* ssrc = wstage + rr0 * kFlStageRow + piece * 16;
+      const size_t gstep = (size_t)kRowsPer * k.units * sizeof(__half) / sizeof(uint4);
+#pragma unroll
+      for (int i = 0; i < 32 / kRowsPer; ++i) {
+        const uint4 val = *reinterpret_cast<const uint4*>(ssrc + i * kRowsPer * kFlStageRow);
+        if (rr0 + i * kRowsPer < live && !(PPK_FL_DBG & 2)) __stcs(gdst + i * gstep, val);
+      }
+      __syncwarp();
     }
-    tc::bulk_wait_all();
   }
 
   tc::fence_before_sync();
