@@ -402,8 +402,44 @@ int ppk_linear_pack(const float* weight, const float* bias, int32_t units, int32
 
 extern "C++" {
 namespace {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// out [rows, units] fp16 as a 2-D tensor; box = one epilogue warp's [32 rows x 64 units] tile, 128B swizzle
+int make_out_map(CUtensorMap* m, void* out, long long rows, int units) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return PPK_ERR_CUDA;
+  const cuuint64_t dims[2] = {(cuuint64_t)units, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)units * sizeof(__half)};
+  const cuuint32_t box[2] = {(cuuint32_t)kFlEpiCols, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? PPK_OK
+             : PPK_ERR_CUDA;
+}
+
 template <int KP>
 int launch_first_layer(const FlArgs& k, cudaStream_t s) {
+  CUtensorMap out_map;
+  int rc = make_out_map(&out_map, k.out, k.rows, k.units);
+  if (rc != PPK_OK) return rc;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(first_layer_kernel<KP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlLayout<KP>::kBytes) !=
@@ -417,8 +453,8 @@ int launch_first_layer(const FlArgs& k, cudaStream_t s) {
   }
   const long long units = ((k.rows + kFlM - 1) / kFlM) * (k.units / kFlN);
   const unsigned grid = (unsigned)(units < 148 ? units : 148);      // persistent: one CTA per SM
-  if (k.activation == PPK_ACT_ELU) first_layer_kernel<KP, 1><<<grid, kFlThreads, FlLayout<KP>::kBytes, s>>>(k);
-  else first_layer_kernel<KP, 0><<<grid, kFlThreads, FlLayout<KP>::kBytes, s>>>(k);
+  if (k.activation == PPK_ACT_ELU) first_layer_kernel<KP, 1><<<grid, kFlThreads, FlLayout<KP>::kBytes, s>>>(k, out_map);
+  else first_layer_kernel<KP, 0><<<grid, kFlThreads, FlLayout<KP>::kBytes, s>>>(k, out_map);
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 }  // namespace

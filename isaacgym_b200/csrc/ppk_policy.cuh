@@ -15,6 +15,7 @@
 //                        -> + bias -> fp16 -> ELU -> fp16 rows, written with bulk stores.  The only GEMM on
 //                        either side of the path; bound by the [rows, units] fp16 write, not by the math.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "ppk_tc.cuh"
@@ -108,7 +109,8 @@ constexpr int kFlEpiCols = kFlN / (kFlEpiWarps / 4);   // accumulator columns pe
 constexpr int kFlThreads = 32 * (2 + kFlPrepWarps + kFlEpiWarps);   // producer, mma, prep, epilogue
 constexpr int kFlALbo = kFlM * 16 + 16;   // +16: the prep warps write 16-byte pieces of different K chunks
 constexpr int kFlBLbo = kFlN * 16;
-constexpr int kFlStageRow = kFlEpiCols * 2 + 16;   // one thread's fp16 outputs of a unit + pad (conflict-free 16-byte stores)
+constexpr int kFlStageRow = kFlEpiCols * 2;        // 128 B: one row of a warp's [32 x 64] fp16 output tile (128B-swizzled)
+static_assert(kFlStageRow == 128, "the output staging tile is laid out for the 128-byte TMA swizzle");
 
 __host__ __device__ constexpr int fl_kpad(int width) { return (width + 15) / 16 * 16; }
 __host__ __device__ constexpr size_t fl_chunk_bytes(int kp) { return (size_t)(kp / 8) * kFlBLbo; }
@@ -118,12 +120,13 @@ struct FlLayout {
   static constexpr int kKc = KP / 8;
   static constexpr int kABytes = kKc * kFlALbo;
   static constexpr int kBBytes = kKc * kFlBLbo;
-  static constexpr int kOffB = 2 * kABytes;
-  static constexpr int kOffStage = kOffB + 2 * kBBytes;
-  static constexpr int kOffCst = kOffStage + 32 * kFlEpiWarps * kFlStageRow;
+  static constexpr int kOffStage = 0;                                  // 1024-byte aligned tiles for the swizzle
+  static constexpr int kOffA = 32 * kFlEpiWarps * kFlStageRow;
+  static constexpr int kOffB = kOffA + 2 * kABytes;
+  static constexpr int kOffCst = kOffB + 2 * kBBytes;
   static constexpr int kOffBar = kOffCst + 2 * KP * 4;
   static constexpr int kBytes = kOffBar + 12 * 8 + 16;
-  static_assert(kOffB % 16 == 0 && kOffStage % 16 == 0 && kOffCst % 16 == 0 && kOffBar % 8 == 0, "alignment");
+  static_assert(kOffA % 16 == 0 && kOffB % 16 == 0 && kOffCst % 16 == 0 && kOffBar % 8 == 0, "alignment");
   static_assert(kBytes <= 227 * 1024, "shared memory budget");
 };
 
@@ -145,6 +148,19 @@ __global__ void linear_pack_kernel(const float* __restrict__ w, const float* __r
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < units; n += gridDim.x * blockDim.x)
     bias_out[n] = bias ? __half2float(__float2half_rn(bias[n])) : 0.0f;
 }
+
+#ifdef PPK_TRACE
+__device__ __forceinline__ void fl_stamp(int slot) {
+  if (g_trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[(size_t)blockIdx.x * 16 + slot] = t;
+  }
+}
+#define FL_STAMP(cond, slot) do { if (cond) fl_stamp(slot); } while (0)
+#else
+#define FL_STAMP(cond, slot)
+#endif
 
 struct FlArgs {
   const float* obs;          // [rows, width]
@@ -169,11 +185,70 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// One operand tile: rows [mt*128, +128) of obs -> clamp -> normalise -> fp16 -> K-major core-matrix layout at
+// `dst`.  An item is one row's 8 consecutive columns (one 16-byte operand piece); consecutive threads take
+// consecutive pieces of a row, so the global loads coalesce.  Columns >= width load 0 and have mean 0 / den 1,
+// rows >= rows produce values nobody stores: no per-element selects.
+template <int KP, int BATCH>
+__device__ __forceinline__ void fl_prep_tile(const FlArgs& k, const float* cst, long long mt, unsigned char* dst, int t,
+                                             int nthreads) {
+  constexpr int kKc = KP / 8, kItems = kFlM * kKc;
+  const bool vec = (k.width % 4 == 0) && ((reinterpret_cast<uintptr_t>(k.obs) & 15u) == 0);
+  const float inf = __int_as_float(0x7f800000);
+  const float clip = k.rms.clip > 0.0f ? k.rms.clip : inf;            // VecTask clipObservations
+  const float lim = k.rms.mean != nullptr ? 5.0f : inf;               // RunningMeanStd output clamp
+  for (int base = t; base < kItems; base += nthreads * BATCH) {
+    float x[BATCH][8];
+    // all loads of the batch first (independent, in flight together), then the arithmetic
+#pragma unroll
+    for (int bi = 0; bi < BATCH; ++bi) {
+      const int item = base + bi * nthreads;
+      const int r = item / kKc, kc = item - r * kKc;
+      const long long row = mt * kFlM + r;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[bi][i] = 0.0f;
+      if (item < kItems && row < k.rows && !(PPK_FL_DBG & 8)) {
+        const float* src = k.obs + row * k.width + kc * 8;
+        if (vec) {
+          if (kc * 8 < k.width) { float4 v = __ldcs(reinterpret_cast<const float4*>(src)); x[bi][0] = v.x; x[bi][1] = v.y; x[bi][2] = v.z; x[bi][3] = v.w; }
+          if (kc * 8 + 4 < k.width) { float4 v = __ldcs(reinterpret_cast<const float4*>(src) + 1); x[bi][4] = v.x; x[bi][5] = v.y; x[bi][6] = v.z; x[bi][7] = v.w; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (kc * 8 + i < k.width) x[bi][i] = __ldcs(src + i);
+        }
+      }
+    }
+#pragma unroll
+    for (int bi = 0; bi < BATCH; ++bi) {
+      const int item = base + bi * nthreads;
+      if (item >= kItems) break;
+      const int r = item / kKc, kc = item - r * kKc;
+      const float4* m4 = reinterpret_cast<const float4*>(cst + kc * 8);
+      const float4* d4 = reinterpret_cast<const float4*>(cst + KP + kc * 8);
+      const float4 ma = m4[0], mb = m4[1], da = d4[0], db = d4[1];
+      const float m[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+      const float d[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = fminf(fmaxf(x[bi][i], -clip), clip);
+        y = (y - m[i]) / d[i];
+        x[bi][i] = fminf(fmaxf(y, -lim), lim);
+      }
+      uint4 pk;
+      pk.x = pack_half2(x[bi][0], x[bi][1]); pk.y = pack_half2(x[bi][2], x[bi][3]);
+      pk.z = pack_half2(x[bi][4], x[bi][5]); pk.w = pack_half2(x[bi][6], x[bi][7]);
+      *reinterpret_cast<uint4*>(dst + kc * kFlALbo + r * 16) = pk;
+    }
+  }
+}
+
 template <int KP, int ACT>
-__global__ void __launch_bounds__(kFlThreads, 1) first_layer_kernel(const __grid_constant__ FlArgs k) {
+__global__ void __launch_bounds__(kFlThreads, 1)
+first_layer_kernel(const __grid_constant__ FlArgs k, const __grid_constant__ CUtensorMap out_map) {
   using L = FlLayout<KP>;
-  extern __shared__ __align__(128) unsigned char fl_smem[];
-  unsigned char* a_s = fl_smem;
+  extern __shared__ __align__(1024) unsigned char fl_smem[];
+  unsigned char* a_s = fl_smem + L::kOffA;
   unsigned char* b_s = fl_smem + L::kOffB;
   unsigned char* stage_s = fl_smem + L::kOffStage;
   float* cst = reinterpret_cast<float*>(fl_smem + L::kOffCst);
@@ -208,6 +283,11 @@ __global__ void __launch_bounds__(kFlThreads, 1) first_layer_kernel(const __grid
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  FL_STAMP(threadIdx.x == 0, 0);
+  // the CTA's first row tile is on the critical path of everything: all warps prepare it together
+  fl_prep_tile<KP, 2>(k, cst, mt_begin, a_s, threadIdx.x, kFlThreads);
+  tc::fence_proxy_async_smem();
+  __syncthreads();
 
   if (warp == 0) {
     // ===== weight-chunk producer: one bulk copy per unit into the 2-deep ring =====
@@ -245,69 +325,35 @@ __global__ void __launch_bounds__(kFlThreads, 1) first_layer_kernel(const __grid
         tc::mma_commit(b_empty + s);
         if (u == u_end - 1 || nc == NC - 1) tc::mma_commit(a_empty + ab);
         tc::mma_commit(acc_full + s);
+        FL_STAMP(it == 0, 3);
+        FL_STAMP(u == u_end - 1, 6);
       }
     }
   } else if (warp < 2 + kFlPrepWarps) {
-    // ===== row-tile preparation: clamp, normalise, fp16, tensor-core operand layout =====
+    // ===== row-tile preparation (tiles after the CTA's first): one tile ahead of the MMA =====
     const int t = threadIdx.x - 64;     // warps 2..5
     const long long mt_last = (u_end - 1) / NC;
-    const bool vec = (k.width % 4 == 0) && ((reinterpret_cast<uintptr_t>(k.obs) & 15u) == 0);
-    for (long long mt = mt_begin; mt <= mt_last && u_begin < u_end; ++mt) {
+    for (long long mt = mt_begin; mt <= mt_last; ++mt) {
       const long long j = mt - mt_begin;
       const int ab = (int)(j & 1), aph = (int)((j >> 1) & 1);
-      mbar_wait_relaxed(a_empty + ab, aph ^ 1);
-      unsigned char* dst = a_s + ab * L::kABytes;
-      constexpr int kItems = kFlM * L::kKc, kStride = 32 * kFlPrepWarps, kBatch = 5;
-      for (int base = t; base < kItems; base += kStride * kBatch) {
-        float x[kBatch][8];
-        // all loads of the batch first (independent, in flight together), then the arithmetic
-#pragma unroll
-        for (int bi = 0; bi < kBatch; ++bi) {
-          const int item = base + bi * kStride;
-          const int r = item / L::kKc, kc = item - r * L::kKc;
-          const long long row = mt * kFlM + r;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) x[bi][i] = 0.0f;
-          if (item < kItems && row < k.rows && !(PPK_FL_DBG & 8)) {
-            const float* src = k.obs + row * k.width + kc * 8;
-            if (vec) {
-              if (kc * 8 < k.width) { float4 v = __ldcs(reinterpret_cast<const float4*>(src)); x[bi][0] = v.x; x[bi][1] = v.y; x[bi][2] = v.z; x[bi][3] = v.w; }
-              if (kc * 8 + 4 < k.width) { float4 v = __ldcs(reinterpret_cast<const float4*>(src) + 1); x[bi][4] = v.x; x[bi][5] = v.y; x[bi][6] = v.z; x[bi][7] = v.w; }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (kc * 8 + i < k.width) x[bi][i] = __ldcs(src + i);
-            }
-          }
-        }
-#pragma unroll
-        for (int bi = 0; bi < kBatch; ++bi) {
-          const int item = base + bi * kStride;
-          if (item >= kItems) break;
-          const int r = item / L::kKc, kc = item - r * L::kKc;
-          const bool live = mt * kFlM + r < k.rows;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int c = kc * 8 + i;
-            float y = clamp_obs(x[bi][i], k.rms.clip);
-            if (k.rms.mean != nullptr) y = fminf(fmaxf((y - cst[c]) / cst[KP + c], -5.0f), 5.0f);
-            x[bi][i] = (live && c < k.width) ? y : 0.0f;
-          }
-          uint4 pk;
-          pk.x = pack_half2(x[bi][0], x[bi][1]); pk.y = pack_half2(x[bi][2], x[bi][3]);
-          pk.z = pack_half2(x[bi][4], x[bi][5]); pk.w = pack_half2(x[bi][6], x[bi][7]);
-          *reinterpret_cast<uint4*>(dst + kc * kFlALbo + r * 16) = pk;
-        }
+      if (j > 0) {                      // tile 0 was prepared by the whole CTA above
+        mbar_wait_relaxed(a_empty + ab, aph ^ 1);
+        fl_prep_tile<KP, 5>(k, cst, mt, a_s + ab * L::kABytes, t, 32 * kFlPrepWarps);
+        tc::fence_proxy_async_smem();
       }
-      tc::fence_proxy_async_smem();
       tc::mbar_arrive(a_full + ab);
+      FL_STAMP(t == 0 && j == 0, 1);
+      FL_STAMP(t == 0 && j == 1, 2);
     }
   } else {
     // ===== epilogue: TMEM -> registers -> + bias -> fp16 -> activation -> fp16 row piece -> bulk store =====
     const int ew = warp - (2 + kFlPrepWarps);
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int cq = ew >> 2;                 // which kFlEpiCols-wide slice of the chunk
-    unsigned char* my_stage = stage_s + (size_t)(ew * 32 + lane) * kFlStageRow;
+    // the warp's [32 rows x 64 units] fp16 tile, 128B-swizzled: 16-byte piece j of row r sits at piece j ^ (r & 7)
+    unsigned char* wstage = stage_s + (size_t)ew * 32 * kFlStageRow;
+    unsigned char* my_row = wstage + lane * kFlStageRow;
+    const int sw = lane & 7;
     for (long long u = u_begin; u < u_end; ++u) {
       const long long it = u - u_begin;
       const int s = (int)(it & 1), ph = (int)((it >> 1) & 1);
@@ -316,7 +362,11 @@ __global__ void __launch_bounds__(kFlThreads, 1) first_layer_kernel(const __grid
       const int col0 = nc * kFlN + cq * kFlEpiCols;
       mbar_wait(acc_full + s, ph);
       tc::fence_after_sync();
+      FL_STAMP(ew == 0 && lane == 0 && it == 0, 4);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kFlN + cq * kFlEpiCols);
+      // the tensor store of the previous unit has finished reading the tile
+      if (lane == 0) tc::bulk_wait_read0();
+      __syncwarp();
 #pragma unroll 1
       for (int g = 0; g < kFlEpiCols / 32; ++g) {
         uint32_t v[32];
@@ -345,36 +395,31 @@ __global__ void __launch_bounds__(kFlThreads, 1) first_layer_kernel(const __grid
             o[2 * i + p] = *reinterpret_cast<uint32_t*>(&lin);
           }
         }
-        uint4* sp = reinterpret_cast<uint4*>(my_stage + g * 64);
-        sp[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        sp[1] = make_uint4(o[4], o[5], o[6], o[7]);
-        sp[2] = make_uint4(o[8], o[9], o[10], o[11]);
-        sp[3] = make_uint4(o[12], o[13], o[14], o[15]);
-      }
-      // the warp's 32 row pieces go out coalesced: per instruction kRowsPer rows, kPieces lanes x 16 B each.
-      // (One bulk store per row was tried first: the copy engine serves ~1 operation per 46 cycles per SM,
-      // 256 of them per unit cost 4x the whole HBM budget.)
-      __syncwarp();
-      const unsigned char* wstage = stage_s + (size_t)(ew * 32) * kFlStageRow;
-      constexpr int kPieces = kFlEpiCols * 2 / 16, kRowsPer = 32 / kPieces;
-      const long long row_w = mt * kFlM + q * 32;
-      const int rr0 = lane / kPieces, piece = lane % kPieces;
-      const int live = (int)min((long long)32, k.rows - row_w);       // rows of this warp that exist
-      uint4* gdst = reinterpret_cast<uint4*>(k.out + (size_t)(row_w + rr0) * k.units + col0) + piece;
-      const unsigned char* ssrc = wstage + rr0 * kFlStageRow + piece * 16;
-      const size_t gstep = (size_t)kRowsPer * k.units * sizeof(__half) / sizeof(uint4);
 #pragma unroll
-      for (int i = 0; i < 32 / kRowsPer; ++i) {
-        const uint4 val = *reinterpret_cast<const uint4*>(ssrc + i * kRowsPer * kFlStageRow);
-        if (rr0 + i * kRowsPer < live && !(PPK_FL_DBG & 2)) __stcs(gdst + i * gstep, val);
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(my_row + (((g * 4 + i) ^ sw) << 4)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
       }
+      // one tensor store per warp and unit (rows past the end of the batch are clipped by the copy engine).
+      // (One 1-D bulk store per ROW was tried first: the engine serves ~1 operation per 46 cycles per SM, and
+      // 256 of them per unit cost 4x the HBM budget; staged, coalesced st.global cost 146 instructions here.)
+      tc::fence_proxy_async_smem();
       __syncwarp();
+      if (lane == 0 && !(PPK_FL_DBG & 2)) {
+        tc::tensor_store_2d(&out_map, col0, (int)(mt * kFlM + q * 32), wstage);
+        tc::bulk_commit();
+      }
+      FL_STAMP(ew == 0 && lane == 0 && it == 0, 5);
+      FL_STAMP(ew == 0 && lane == 0 && it == 8, 9);
+      FL_STAMP(ew == 0 && lane == 0 && it == 16, 10);
+      FL_STAMP(ew == 0 && lane == 0 && u == u_end - 1, 7);
     }
+    if (lane == 0) tc::bulk_wait_all();
   }
 
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  FL_STAMP(threadIdx.x == 0, 8);
   if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
 }
 

@@ -51,7 +51,8 @@ def main():
     t = timeit(lambda: rms.normalize(nxt(), out32))
     print(json.dumps({"kernel": "rms_normalize", "rows": rows, "us": t * 1e6, "hbm_frac": rows * width * 8 / t / 1e9 / PEAK}))
     rms.eval()
-    for units in (2048, 4096):
+    unit_list = [int(u) for u in sys.argv[3].split(',')] if len(sys.argv) > 3 else [2048, 4096]
+    for units in unit_list:
         w = torch.randn(units, width, device=dev, generator=g) / width ** 0.5
         b = torch.randn(units, device=dev, generator=g) * 0.1
         layer = FirstLayer(w, b, "elu", rms)
