@@ -384,7 +384,7 @@ int ppk_rms_normalize(const PpkRunningMeanStd* rms, const float* obs, int64_t ro
 
 size_t ppk_linear_packed_bytes(int32_t units, int32_t width) {
   if (units <= 0 || width <= 0 || units % kFlN != 0) return 0;
-  return (size_t)units * fl_kpad(width) * sizeof(__half) + (size_t)units * sizeof(float);
+  return (size_t)units * fl_kpad(width) * sizeof(__half);
 }
 
 int ppk_linear_pack(const float* weight, const float* bias, int32_t units, int32_t width, void* packed, size_t packed_bytes,
@@ -394,9 +394,8 @@ int ppk_linear_pack(const float* weight, const float* bias, int32_t units, int32
   if (need == 0 || packed_bytes < need) return PPK_ERR_SHAPE;
   if (reinterpret_cast<uintptr_t>(packed) & 15u) return PPK_ERR_ALIGN;
   const int kp = fl_kpad(width);
-  __half* ph = static_cast<__half*>(packed);
-  float* pb = reinterpret_cast<float*>(static_cast<unsigned char*>(packed) + (size_t)units * kp * sizeof(__half));
-  linear_pack_kernel<<<148 * 2, 256, 0, static_cast<cudaStream_t>(stream)>>>(weight, bias, units, width, kp, ph, pb);
+  linear_pack_kernel<<<148 * 2, 256, 0, static_cast<cudaStream_t>(stream)>>>(weight, bias, units, width, kp,
+                                                                              static_cast<__half*>(packed));
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 
@@ -479,7 +478,6 @@ int ppk_policy_first_layer(const PpkRunningMeanStd* rms, const float* obs, int64
   const int kp = fl_kpad(width);
   k.obs = obs; k.rows = rows; k.width = width; k.units = units; k.activation = activation;
   k.packed = static_cast<const unsigned char*>(packed);
-  k.bias = reinterpret_cast<const float*>(k.packed + (size_t)units * kp * sizeof(__half));
   k.out = static_cast<__half*>(out_f16);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (kp) {

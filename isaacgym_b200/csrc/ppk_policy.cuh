@@ -103,7 +103,7 @@ __global__ void rms_apply_kernel(RmsArgs a, const float* __restrict__ obs, long 
 #endif
 constexpr int kFlM = 128;            // rows per tile = TMEM lanes
 constexpr int kFlN = 256;            // units per chunk = fp32 accumulator columns per buffer
-constexpr int kFlPrepWarps = 4;
+constexpr int kFlPrepWarps = 8;          // latency-bound (global loads) and competing with 16 epilogue warps for issue slots
 constexpr int kFlEpiWarps = 16;          // four per TMEM lane quarter: the epilogue is latency-bound per warp
 constexpr int kFlEpiCols = kFlN / (kFlEpiWarps / 4);   // accumulator columns per epilogue warp and unit
 constexpr int kFlThreads = 32 * (2 + kFlPrepWarps + kFlEpiWarps);   // producer, mma, prep, epilogue
@@ -112,7 +112,10 @@ constexpr int kFlBLbo = kFlN * 16;
 constexpr int kFlStageRow = kFlEpiCols * 2;        // 128 B: one row of a warp's [32 x 64] fp16 output tile (128B-swizzled)
 static_assert(kFlStageRow == 128, "the output staging tile is laid out for the 128-byte TMA swizzle");
 
-__host__ __device__ constexpr int fl_kpad(int width) { return (width + 15) / 16 * 16; }
+// K is padded to a multiple of 16 with at least ONE spare column: column `width` of the row tile is the
+// constant 1 and column `width` of the weights is the bias, so the bias add happens inside the MMA (fp32
+// accumulation either way) instead of costing the epilogue an add and a load per element.
+__host__ __device__ constexpr int fl_kpad(int width) { return (width + 1 + 15) / 16 * 16; }
 __host__ __device__ constexpr size_t fl_chunk_bytes(int kp) { return (size_t)(kp / 8) * kFlBLbo; }
 
 template <int KP>
@@ -124,15 +127,15 @@ struct FlLayout {
   static constexpr int kOffA = 32 * kFlEpiWarps * kFlStageRow;
   static constexpr int kOffB = kOffA + 2 * kABytes;
   static constexpr int kOffCst = kOffB + 2 * kBBytes;
-  static constexpr int kOffBar = kOffCst + 2 * KP * 4;
+  static constexpr int kOffBar = kOffCst + 3 * KP * 4;      // mean, den, 1/den per column
   static constexpr int kBytes = kOffBar + 12 * 8 + 16;
   static_assert(kOffA % 16 == 0 && kOffB % 16 == 0 && kOffCst % 16 == 0 && kOffBar % 8 == 0, "alignment");
   static_assert(kBytes <= 227 * 1024, "shared memory budget");
 };
 
-// packed weight blob: [units/256 chunks][KP/8][256][8] fp16, then bias [units] as fp32 values of the fp16-rounded bias
+// packed weight blob: [units/256 chunks][KP/8][256][8] fp16; column `width` holds the bias, the rest of the pad is 0
 __global__ void linear_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias, int units, int width, int kp,
-                                   __half* __restrict__ packed, float* __restrict__ bias_out) {
+                                   __half* __restrict__ packed) {
   const long long total = (long long)units * kp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     // i enumerates the packed order
@@ -143,10 +146,11 @@ __global__ void linear_pack_kernel(const float* __restrict__ w, const float* __r
     const int kc = (int)(t2 % (kp / 8));
     const int chunk = (int)(t2 / (kp / 8));
     const int n = chunk * kFlN + nl, k = kc * 8 + j;
-    packed[i] = __float2half_rn(k < width ? w[(size_t)n * width + k] : 0.0f);
+    float v = 0.0f;
+    if (k < width) v = w[(size_t)n * width + k];
+    else if (k == width && bias != nullptr) v = bias[n];
+    packed[i] = __float2half_rn(v);
   }
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < units; n += gridDim.x * blockDim.x)
-    bias_out[n] = bias ? __half2float(__float2half_rn(bias[n])) : 0.0f;
 }
 
 #ifdef PPK_TRACE
@@ -168,7 +172,6 @@ struct FlArgs {
   int width, units, activation;   // activation: 0 none, 1 ELU
   RmsArgs rms;               // rms.mean == nullptr: no normalisation
   const unsigned char* packed;
-  const float* bias;         // inside the packed blob
   __half* out;               // [rows, units]
 };
 
@@ -183,6 +186,16 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// n / d with r = RN(1/d) computed once per column: quotient estimate plus two exact-residual corrections
+// (the refinement div.rn itself performs, minus its range checks: |n| and d are ordinary normal numbers
+// here).  Five instructions instead of the dozen of a generic IEEE division, same result.
+__device__ __forceinline__ float div_by_const(float n, float d, float r) {
+  float q = n * r;
+  q = fmaf(fmaf(-d, q, n), r, q);
+  q = fmaf(fmaf(-d, q, n), r, q);
+  return q;
 }
 
 // One operand tile: rows [mt*128, +128) of obs -> clamp -> normalise -> fp16 -> K-major core-matrix layout at
@@ -226,14 +239,16 @@ __device__ __forceinline__ void fl_prep_tile(const FlArgs& k, const float* cst, 
       const int r = item / kKc, kc = item - r * kKc;
       const float4* m4 = reinterpret_cast<const float4*>(cst + kc * 8);
       const float4* d4 = reinterpret_cast<const float4*>(cst + KP + kc * 8);
-      const float4 ma = m4[0], mb = m4[1], da = d4[0], db = d4[1];
+      const float4* r4 = reinterpret_cast<const float4*>(cst + 2 * KP + kc * 8);
+      const float4 ma = m4[0], mb = m4[1], da = d4[0], db = d4[1], ra = r4[0], rb = r4[1];
       const float m[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
       const float d[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+      const float rc[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float y = fminf(fmaxf(x[bi][i], -clip), clip);
-        y = (y - m[i]) / d[i];
-        x[bi][i] = fminf(fmaxf(y, -lim), lim);
+        float y = x[bi][i];
+        if (k.rms.clip > 0.0f) y = fminf(fmaxf(y, -clip), clip);
+        x[bi][i] = fminf(fmaxf(div_by_const(y - m[i], d[i], rc[i]), -lim), lim);
       }
       uint4 pk;
       pk.x = pack_half2(x[bi][0], x[bi][1]); pk.y = pack_half2(x[bi][2], x[bi][3]);
@@ -276,8 +291,10 @@ first_layer_kernel(const __grid_constant__ FlArgs k, const __grid_constant__ CUt
   // normalisation constants: float(mean), sqrt(float(var) + eps)
   for (int c = threadIdx.x; c < KP; c += kFlThreads) {
     const bool on = k.rms.mean != nullptr && c < k.width;
-    cst[c] = on ? (float)k.rms.mean[c] : 0.0f;
-    cst[KP + c] = on ? sqrtf((float)k.rms.var[c] + k.rms.eps) : 1.0f;
+    cst[c] = on ? (float)k.rms.mean[c] : (c == k.width ? -1.0f : 0.0f);      // column `width`: (0 - -1) / 1 = the bias column's 1
+    const float den = on ? sqrtf((float)k.rms.var[c] + k.rms.eps) : 1.0f;
+    cst[KP + c] = den;
+    cst[2 * KP + c] = 1.0f / den;
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -331,14 +348,20 @@ first_layer_kernel(const __grid_constant__ FlArgs k, const __grid_constant__ CUt
     }
   } else if (warp < 2 + kFlPrepWarps) {
     // ===== row-tile preparation (tiles after the CTA's first): one tile ahead of the MMA =====
-    const int t = threadIdx.x - 64;     // warps 2..5
+    const int t = threadIdx.x - 64;     // warps 2..9
     const long long mt_last = (u_end - 1) / NC;
     for (long long mt = mt_begin; mt <= mt_last; ++mt) {
       const long long j = mt - mt_begin;
       const int ab = (int)(j & 1), aph = (int)((j >> 1) & 1);
+      if (mt < mt_last) {               // pull the tile after this one into L2 while this one is worked on
+        const long long r0 = (mt + 1) * kFlM;
+        const long long bytes = (min((long long)kFlM, k.rows - r0)) * k.width * 4;
+        const char* p = reinterpret_cast<const char*>(k.obs + r0 * k.width);
+        for (long long off = (long long)t * 128; off < bytes; off += 128LL * 32 * kFlPrepWarps) prefetch_l2(p + off);
+      }
       if (j > 0) {                      // tile 0 was prepared by the whole CTA above
         mbar_wait_relaxed(a_empty + ab, aph ^ 1);
-        fl_prep_tile<KP, 5>(k, cst, mt, a_s + ab * L::kABytes, t, 32 * kFlPrepWarps);
+        fl_prep_tile<KP, 3>(k, cst, mt, a_s + ab * L::kABytes, t, 32 * kFlPrepWarps);
         tc::fence_proxy_async_smem();
       }
       tc::mbar_arrive(a_full + ab);
@@ -376,13 +399,11 @@ first_layer_kernel(const __grid_constant__ FlArgs k, const __grid_constant__ CUt
           tc::fence_before_sync();
           tc::mbar_arrive(acc_empty + s);
         }
-        const float4* b4 = reinterpret_cast<const float4*>(k.bias + col0 + g * 32);
         uint32_t o[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b = __ldg(b4 + i);
-          float f[4] = {__uint_as_float(v[4 * i]) + b.x, __uint_as_float(v[4 * i + 1]) + b.y,
-                        __uint_as_float(v[4 * i + 2]) + b.z, __uint_as_float(v[4 * i + 3]) + b.w};
+          const float f[4] = {__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                              __uint_as_float(v[4 * i + 3])};       // bias already inside (K padding column)
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
             __half2 lin = __floats2half2_rn(f[2 * p], f[2 * p + 1]);     // the fp16 output of the linear layer

@@ -101,8 +101,8 @@ def test_product_never_imports_the_oracle():
 
 
 def test_learner_side_argument_validation(lib):
-    assert lib.ppk_linear_packed_bytes(2048, 80) == 2048 * 80 * 2 + 2048 * 4
-    assert lib.ppk_linear_packed_bytes(2048, 94) == 2048 * 96 * 2 + 2048 * 4      # K padded to a multiple of 16
+    assert lib.ppk_linear_packed_bytes(2048, 80) == 2048 * 96 * 2      # K padded to a multiple of 16 with room for the bias column
+    assert lib.ppk_linear_packed_bytes(2048, 94) == 2048 * 96 * 2
     assert lib.ppk_linear_packed_bytes(1000, 80) == 0                             # units % 256 != 0
     rms = N.PpkRunningMeanStd()
     rms.struct_size = C.sizeof(N.PpkRunningMeanStd)
@@ -111,7 +111,7 @@ def test_learner_side_argument_validation(lib):
     rms.struct_size = 8
     assert lib.ppk_rms_normalize(rms, 0x1000, 16, 0x1000, None) == -6             # PPK_ERR_ABI
     assert lib.ppk_policy_first_layer(None, 0x1000, 16, 80, 0x1000, 1000, 1, 0x1000, None) == -2   # units
-    assert lib.ppk_policy_first_layer(None, 0x1000, 16, 313, 0x1000, 2048, 1, 0x1000, None) == -2  # width > 96
+    assert lib.ppk_policy_first_layer(None, 0x1000, 16, 313, 0x1000, 2048, 1, 0x1000, None) == -2  # width > 95
     assert lib.ppk_policy_first_layer(None, 0x1000, 16, 80, 0x1000, 2048, 7, 0x1000, None) == -4   # activation
     assert lib.ppk_policy_first_layer(None, None, 16, 80, 0x1000, 2048, 1, 0x1000, None) == -1
     assert lib.ppk_policy_first_layer(None, 0x1000, 0, 80, 0x1000, 2048, 1, 0x1000, None) == 0     # empty batch
