@@ -127,6 +127,46 @@ def physical_gpu_index(local_rank):
     return local_rank
 
 
+def run_learner_side(tasks, units, peak, iters=40, warm=5):
+    """SURVEY 8(f) rank 4 on the obs_buf the task step just wrote: RunningMeanStd update, and the fused
+    normalise + first MLP layer (fp16 out).  CUDA events; the obs sets rotate, the fp16 output (rows x units
+    x 2 B) is larger than L2 by itself."""
+    import torch
+    from isaacgym_b200.policy_input import FirstLayer, RunningMeanStd
+    obs = [t.obs_buf.view(t.obs_buf.shape[0], -1) if t.obs_buf.dim() == 2 else None for t in tasks]
+    if any(o is None for o in obs):
+        return {"skipped": "obs_buf is not [N, num_obs]"}
+    rows, width = obs[0].shape
+    dev = obs[0].device
+    g = torch.Generator(device=dev).manual_seed(0)
+    rms = RunningMeanStd(width, device=dev)
+    w = torch.randn(units, width, device=dev, generator=g) / width ** 0.5
+    b = torch.randn(units, device=dev, generator=g) * 0.1
+    layer = FirstLayer(w, b, "elu", rms)
+    out = torch.empty(rows, units, dtype=torch.float16, device=dev)
+    res = {}
+    for name, fn in (("rms_update", lambda o: rms.update(o)), ("first_layer", lambda o: layer(o, out))):
+        if name == "first_layer":
+            rms.eval()
+        for i in range(warm):
+            fn(obs[i % len(obs)])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(obs[i % len(obs)])
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3 / iters
+        nbytes = rows * width * 4 + (rows * units * 2 if name == "first_layer" else 0)
+        res[name] = {"us": sec * 1e6, "rows_per_s": rows / sec, "achieved_gbs": nbytes / sec / 1e9,
+                     "roofline_frac": nbytes / sec / 1e9 / peak}
+    res["first_layer"].update({"units": units, "dtype": "f16 operands, f32 accumulate (tcgen05), f16 out",
+                               "tflops": 2.0 * rows * width * units / (res["first_layer"]["us"] * 1e-6) / 1e12,
+                               "bound": "hbm (the [rows, units] fp16 write)"})
+    return res
+
+
 def make_tasks(variant, n, sets, device, seed_base):
     from isaacgym_b200.config import CONFIGS
     from isaacgym_b200.synth import make_state
@@ -334,6 +374,12 @@ def main():
                              "ends and reach DRAM later, so the step's real traffic is ~1.36 kB/env vs 726 B algorithmic"},
         "stats_sample": {k: stat_means[k] for k in ("reward_sum", "progress_sum", "reset_count")},
     }
+    if rank == 0 and not args.no_extras and variant != "base":
+        # the learner side of the path, context only
+        try:
+            line["learner_side"] = run_learner_side(tasks, 2048, peak)
+        except Exception as e:  # noqa: BLE001
+            line["learner_side"] = {"error": str(e)[:200]}
     del tasks
     torch.cuda.empty_cache()
 

@@ -344,7 +344,7 @@ int ppk_rms_accumulate(const PpkRunningMeanStd* rms, const float* obs, int64_t r
   if (!obs || !rms->moments) return PPK_ERR_NULL;
   const int R = a.width >= 512 ? 1 : 512 / a.width;       // rows per CTA pass
   long long blocks = (rows + (long long)R * 16 - 1) / ((long long)R * 16);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148) blocks = 148;       // one CTA per SM: 2 fp64 atomics per column and CTA onto 2*width addresses
   if (blocks < 1) blocks = 1;
   const size_t smem = sizeof(double) * 2 * R * a.width;
   rms_moments_kernel<<<(unsigned)blocks, dim3(a.width, R), smem, static_cast<cudaStream_t>(stream)>>>(

@@ -34,6 +34,7 @@ class RunningMeanStd:
         self._moments = torch.zeros(2 * self.insize, dtype=torch.float64, device=self.device)
         self.training = True
         self._lib = N.load()
+        self._s = self._make_struct()           # the buffers never move: build the descriptor once
 
     def train(self, mode: bool = True):
         self.training = bool(mode)
@@ -43,6 +44,13 @@ class RunningMeanStd:
         return self.train(False)
 
     def _struct(self) -> N.PpkRunningMeanStd:
+        s = self._s                              # refreshed each call: callers may rebind the buffers
+        s.clip_obs, s.epsilon = self.clip_obs, self.epsilon
+        s.running_mean, s.running_var = self.running_mean.data_ptr(), self.running_var.data_ptr()
+        s.count = self.count.data_ptr()
+        return s
+
+    def _make_struct(self) -> N.PpkRunningMeanStd:
         s = N.PpkRunningMeanStd()
         s.struct_size = C.sizeof(N.PpkRunningMeanStd)
         s.width, s.epsilon, s.clip_obs = self.insize, self.epsilon, self.clip_obs
