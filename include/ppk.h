@@ -257,8 +257,8 @@ PPK_API int ppk_host_session_traffic(const PpkHostSession* s, int64_t* h2d_bytes
  * (rl_games/algos_torch/running_mean_std.py; un-vendored, restated in oracle/policy_oracle.py):
  * fp64 running_mean / running_var [width] and count [1], epsilon 1e-5, output clamped to +-5.
  * `clip_obs` is VecTask.step's clamp of obs_buf (clipObservations; <= 0 = none = upstream default inf).
- * `moments` is a caller-owned, zero-initialised fp64 scratch of 2*width entries (column sums and sums
- * of squares of the batches not yet merged). */
+ * `moments` is a caller-owned, zero-initialised fp64 scratch of 2*width + 1 entries (column sums and sums
+ * of squares of the batches not yet merged, and a ticket word). */
 typedef struct PpkRunningMeanStd {
   uint32_t struct_size;
   int32_t width;

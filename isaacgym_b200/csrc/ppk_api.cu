@@ -327,11 +327,40 @@ namespace {
 int rms_args(const PpkRunningMeanStd* r, RmsArgs* a) {
   if (r == nullptr) return PPK_ERR_NULL;
   if (r->struct_size != sizeof(PpkRunningMeanStd)) return PPK_ERR_ABI;
-  if (r->width <= 0 || r->width > 1024) return PPK_ERR_SHAPE;
+  if (r->width <= 0 || r->width > 512) return PPK_ERR_SHAPE;
   if (!r->running_mean || !r->running_var || !r->count) return PPK_ERR_NULL;
   a->width = r->width; a->eps = r->epsilon; a->clip = r->clip_obs;
   a->mean = r->running_mean; a->var = r->running_var; a->count = r->count;
   return PPK_OK;
+}
+}  // namespace
+
+namespace {
+// thread layout of the rms kernels: x = column group (4 columns when the rows are 16-byte aligned), y = rows
+int rms_launch_moments(const PpkRunningMeanStd* rms, const RmsArgs& a, const float* obs, int64_t rows, int merge,
+                       cudaStream_t s) {
+  const bool vec = (a.width % 4 == 0) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0);
+  const int wx = vec ? a.width / 4 : a.width;
+  int R = 512 / wx;
+  if (R < 1) R = 1;
+  if (R < (vec ? 8 : 2)) R = (wx * (vec ? 8 : 2) <= 1024) ? (vec ? 8 : 2) : R;     // the fold needs 2*VEC row slots
+  long long blocks = (rows + (long long)R * 4 - 1) / ((long long)R * 4);
+  if (blocks > 148) blocks = 148;       // one CTA per SM: 2 fp64 atomics per column and CTA
+  if (blocks < 1) blocks = 1;
+  const size_t smem = sizeof(double) * 2 * (vec ? 4 : 1) * R * wx;
+  if (vec) {
+    if (R < 8) return PPK_ERR_SHAPE;
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(rms_moments_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      configured = true;
+    }
+    rms_moments_kernel<4><<<(unsigned)blocks, dim3(wx, R), smem, s>>>(a, obs, rows, rms->moments, merge, (double)rows);
+  } else {
+    if (R < 2) return PPK_ERR_SHAPE;
+    rms_moments_kernel<1><<<(unsigned)blocks, dim3(wx, R), smem, s>>>(a, obs, rows, rms->moments, merge, (double)rows);
+  }
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 }  // namespace
 
@@ -342,14 +371,7 @@ int ppk_rms_accumulate(const PpkRunningMeanStd* rms, const float* obs, int64_t r
   if (rows < 0) return PPK_ERR_SHAPE;
   if (rows == 0) return PPK_OK;
   if (!obs || !rms->moments) return PPK_ERR_NULL;
-  const int R = a.width >= 512 ? 1 : 512 / a.width;       // rows per CTA pass
-  long long blocks = (rows + (long long)R * 16 - 1) / ((long long)R * 16);
-  if (blocks > 148) blocks = 148;       // one CTA per SM: 2 fp64 atomics per column and CTA onto 2*width addresses
-  if (blocks < 1) blocks = 1;
-  const size_t smem = sizeof(double) * 2 * R * a.width;
-  rms_moments_kernel<<<(unsigned)blocks, dim3(a.width, R), smem, static_cast<cudaStream_t>(stream)>>>(
-      obs, rows, a.width, a.clip, rms->moments);
-  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+  return rms_launch_moments(rms, a, obs, rows, 0, static_cast<cudaStream_t>(stream));
 }
 
 int ppk_rms_merge(const PpkRunningMeanStd* rms, double batch_rows, void* stream) {
@@ -363,10 +385,13 @@ int ppk_rms_merge(const PpkRunningMeanStd* rms, double batch_rows, void* stream)
 }
 
 int ppk_rms_update(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, void* stream) {
-  if (rows == 0) return rms ? PPK_OK : PPK_ERR_NULL;
-  int rc = ppk_rms_accumulate(rms, obs, rows, stream);
+  RmsArgs a;
+  int rc = rms_args(rms, &a);
   if (rc != PPK_OK) return rc;
-  return ppk_rms_merge(rms, (double)rows, stream);
+  if (rows < 0) return PPK_ERR_SHAPE;
+  if (rows == 0) return PPK_OK;
+  if (!obs || !rms->moments) return PPK_ERR_NULL;
+  return rms_launch_moments(rms, a, obs, rows, 1, static_cast<cudaStream_t>(stream));     // moments + merge, one launch
 }
 
 int ppk_rms_normalize(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, float* out, void* stream) {
@@ -376,9 +401,15 @@ int ppk_rms_normalize(const PpkRunningMeanStd* rms, const float* obs, int64_t ro
   if (rows < 0) return PPK_ERR_SHAPE;
   if (rows == 0) return PPK_OK;
   if (!obs || !out) return PPK_ERR_NULL;
-  long long blocks = (rows * a.width + 255) / 256;
+  const bool vec = (a.width % 4 == 0) && (((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0);
+  const int wx = vec ? a.width / 4 : a.width;
+  int R = 256 / wx;
+  if (R < 1) R = 1;
+  long long blocks = (rows + R - 1) / R;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  rms_apply_kernel<<<(unsigned)blocks, 256, sizeof(float) * 2 * a.width, static_cast<cudaStream_t>(stream)>>>(a, obs, rows, out);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (vec) rms_apply_kernel<4><<<(unsigned)blocks, dim3(wx, R), 0, s>>>(a, obs, rows, out);
+  else rms_apply_kernel<1><<<(unsigned)blocks, dim3(wx, R), 0, s>>>(a, obs, rows, out);
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 

@@ -35,63 +35,124 @@ struct RmsArgs {
 
 __device__ __forceinline__ float clamp_obs(float x, float clip) { return clip > 0.0f ? fminf(fmaxf(x, -clip), clip) : x; }
 
-// grid-stride over row blocks; threadIdx.x = column, threadIdx.y = row inside the block of rows.
-// sums[0..W) += sum_r x, sums[W..2W) += sum_r x^2 (fp64 atomics, a few per CTA and column)
-__global__ void rms_moments_kernel(const float* __restrict__ obs, long long rows, int width, float clip, double* sums) {
-  extern __shared__ double red[];            // [2][blockDim.y][width]
-  const int c = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
-  double s = 0.0, ss = 0.0;
-  if (c < width) {
-    for (long long r = (long long)blockIdx.x * R + ry; r < rows; r += (long long)gridDim.x * R) {
-      const float x = clamp_obs(__ldcs(obs + r * width + c), clip);
-      s += (double)x;
-      ss += (double)x * (double)x;
-    }
-    red[ry * width + c] = s;
-    red[(R + ry) * width + c] = ss;
-  }
-  __syncthreads();
-  if (ry == 0 && c < width) {
-    for (int y = 1; y < R; ++y) { s += red[y * width + c]; ss += red[(R + y) * width + c]; }
-    atomicAdd(sums + c, s);
-    atomicAdd(sums + width + c, ss);
-  }
+// RunningMeanStd._update_mean_var_count_from_moments for one column, batch mean / unbiased batch variance
+// from the fp64 sums; clears the sums for the next batch.
+__device__ __forceinline__ void rms_merge_column(const RmsArgs& a, double* sums, double batch_rows, double count, int c) {
+  const double S = __ldcg(sums + c), SS = __ldcg(sums + a.width + c);      // written by L2 atomics
+  const double bmean = S / batch_rows;
+  const double bvar = (SS - S * bmean) / (batch_rows - 1.0);   // torch.var: correction = 1 (nan for one row, as torch)
+  const double delta = bmean - a.mean[c];
+  const double tot = count + batch_rows;
+  const double m2 = a.var[c] * count + bvar * batch_rows + delta * delta * count * batch_rows / tot;
+  a.mean[c] = a.mean[c] + delta * batch_rows / tot;
+  a.var[c] = m2 / tot;
+  sums[c] = 0.0;
+  sums[a.width + c] = 0.0;
 }
 
-// RunningMeanStd._update_mean_var_count_from_moments with batch mean / unbiased batch variance from
-// the fp64 sums; clears the sums for the next batch.  One CTA.
+// Column sums and sums of squares of obs [rows, width] in fp64.  VEC = 4: threadIdx.x owns four adjacent
+// columns (one 16-byte load per row), threadIdx.y walks the rows; four rows in flight per thread.
+// sums[0..W) += sum_r x, sums[W..2W) += sum_r x^2 (two fp64 atomics per column and CTA).  With merge != 0 the
+// last CTA to finish (ticket in sums[2W]) folds the batch into the running statistics: one launch per update.
+template <int VEC>
+__global__ void rms_moments_kernel(RmsArgs a, const float* __restrict__ obs, long long rows, double* sums, int merge,
+                                   double batch_rows) {
+  extern __shared__ double red[];            // [2 * VEC][blockDim.y][blockDim.x]
+  const int cx = threadIdx.x, ry = threadIdx.y, R = blockDim.y, WX = blockDim.x;
+  const int width = a.width;
+  const bool on = cx * VEC < width;
+  double s[VEC], ss[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) s[v] = ss[v] = 0.0;
+  if (on) {
+    const long long step = (long long)gridDim.x * R;
+    long long r = (long long)blockIdx.x * R + ry;
+    constexpr int U = 4;
+    for (; r + (U - 1) * step < rows; r += U * step) {
+      float x[U][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float* p = obs + (r + u * step) * width + cx * VEC;
+        if (VEC == 4) { const float4 t = __ldcs(reinterpret_cast<const float4*>(p)); x[u][0] = t.x; x[u][1] = t.y; x[u][2] = t.z; x[u][VEC - 1] = t.w; }
+        else x[u][0] = __ldcs(p);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const double d = (double)clamp_obs(x[u][v], a.clip);
+          s[v] += d;
+          ss[v] += d * d;
+        }
+    }
+    for (; r < rows; r += step)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const double d = (double)clamp_obs(__ldcs(obs + r * width + cx * VEC + v), a.clip);
+        s[v] += d;
+        ss[v] += d * d;
+      }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      red[((2 * v) * R + ry) * WX + cx] = s[v];
+      red[((2 * v + 1) * R + ry) * WX + cx] = ss[v];
+    }
+  }
+  __syncthreads();
+  // thread (cx, ry < 2*VEC) folds one of the 2*VEC partial arrays of column group cx
+  if (on && ry < 2 * VEC) {
+    double t = 0.0;
+    for (int y = 0; y < R; ++y) t += red[(ry * R + y) * WX + cx];
+    const int v = ry >> 1;
+    atomicAdd(sums + ((ry & 1) ? width : 0) + cx * VEC + v, t);
+  }
+  if (!merge) return;
+  __shared__ unsigned int last;
+  __threadfence();
+  __syncthreads();
+  if (cx == 0 && ry == 0) {
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(sums + 2 * width);
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    if (last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const double count = *a.count;
+  __syncthreads();
+  for (int c = ry * WX + cx; c < width; c += R * WX) rms_merge_column(a, sums, batch_rows, count, c);
+  if (cx == 0 && ry == 0) *a.count = count + batch_rows;
+}
+
+// stand-alone merge (after the ranks all-reduced the moments).  One CTA.
 __global__ void rms_merge_kernel(RmsArgs a, double* sums, double batch_rows) {
   const double count = *a.count;
   __syncthreads();
-  for (int c = threadIdx.x; c < a.width; c += blockDim.x) {
-    const double S = sums[c], SS = sums[a.width + c];
-    const double bmean = S / batch_rows;
-    const double bvar = (SS - S * bmean) / (batch_rows - 1.0);   // torch.var: correction = 1 (nan for one row, as torch)
-    const double delta = bmean - a.mean[c];
-    const double tot = count + batch_rows;
-    const double m2 = a.var[c] * count + bvar * batch_rows + delta * delta * count * batch_rows / tot;
-    a.mean[c] = a.mean[c] + delta * batch_rows / tot;
-    a.var[c] = m2 / tot;
-    sums[c] = 0.0;
-    sums[a.width + c] = 0.0;
-  }
+  for (int c = threadIdx.x; c < a.width; c += blockDim.x) rms_merge_column(a, sums, batch_rows, count, c);
   if (threadIdx.x == 0) *a.count = count + batch_rows;
 }
 
-// y = clamp((clamp(x) - float(mean)) / sqrt(float(var) + eps), -5, 5), fp32
+// y = clamp((clamp(x) - float(mean)) / sqrt(float(var) + eps), -5, 5), fp32; same thread layout as the moments
+template <int VEC>
 __global__ void rms_apply_kernel(RmsArgs a, const float* __restrict__ obs, long long rows, float* __restrict__ out) {
-  extern __shared__ float cst[];      // mean[width], den[width]
-  for (int c = threadIdx.x; c < a.width; c += blockDim.x) {
-    cst[c] = (float)a.mean[c];
-    cst[a.width + c] = sqrtf((float)a.var[c] + a.eps);
+  const int cx = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
+  if (cx * VEC >= a.width) return;
+  float m[VEC], d[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    m[v] = (float)a.mean[cx * VEC + v];
+    d[v] = sqrtf((float)a.var[cx * VEC + v] + a.eps);
   }
-  __syncthreads();
-  const long long total = rows * a.width;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(e % a.width);
-    const float x = clamp_obs(__ldcs(obs + e), a.clip);
-    const float y = (x - cst[c]) / cst[a.width + c];
-    __stcs(out + e, fminf(fmaxf(y, -5.0f), 5.0f));
+  const long long step = (long long)gridDim.x * R;
+  for (long long r = (long long)blockIdx.x * R + ry; r < rows; r += step) {
+    const long long off = r * a.width + cx * VEC;
+    float x[VEC];
+    if (VEC == 4) { const float4 t = __ldcs(reinterpret_cast<const float4*>(obs + off)); x[0] = t.x; x[1] = t.y; x[2] = t.z; x[VEC - 1] = t.w; }
+    else x[0] = __ldcs(obs + off);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) x[v] = fminf(fmaxf((clamp_obs(x[v], a.clip) - m[v]) / d[v], -5.0f), 5.0f);
+    if (VEC == 4) __stcs(reinterpret_cast<float4*>(out + off), make_float4(x[0], x[1], x[2], x[VEC - 1]));
+    else __stcs(out + off, x[0]);
   }
 }
 

@@ -31,7 +31,7 @@ class RunningMeanStd:
         self.running_mean = torch.zeros(self.insize, dtype=torch.float64, device=self.device)
         self.running_var = torch.ones(self.insize, dtype=torch.float64, device=self.device)
         self.count = torch.ones((), dtype=torch.float64, device=self.device)
-        self._moments = torch.zeros(2 * self.insize, dtype=torch.float64, device=self.device)
+        self._moments = torch.zeros(2 * self.insize + 1, dtype=torch.float64, device=self.device)
         self.training = True
         self._lib = N.load()
         self._s = self._make_struct()           # the buffers never move: build the descriptor once
@@ -74,7 +74,7 @@ class RunningMeanStd:
         import torch.distributed as dist
         N.check(self._lib.ppk_rms_accumulate(s, x.data_ptr(), x.shape[0], N.current_stream_ptr()), "rms_accumulate")
         rows = torch.tensor([float(x.shape[0])], dtype=torch.float64, device=self.device)
-        dist.all_reduce(self._moments, group=group)
+        dist.all_reduce(self._moments[:2 * self.insize], group=group)
         dist.all_reduce(rows, group=group)
         N.check(self._lib.ppk_rms_merge(s, float(rows.item()), N.current_stream_ptr()), "rms_merge")
 
