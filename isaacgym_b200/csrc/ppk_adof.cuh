@@ -71,8 +71,11 @@ __device__ __forceinline__ void adof_wait() { asm volatile("bar.sync 2, %0;" ::"
 
 constexpr uint32_t kPhaseDeferCounterClear = 1u << 8;   // internal (host session): clear counters once per shard
 
+#ifndef PPK_ADOF_MINB
+#define PPK_ADOF_MINB 8        // CTAs per SM with the compact reference pose (27 KB smem, 48 registers)
+#endif
 template <bool COMPACT>
-__global__ void __launch_bounds__(kAdofThreads, 6)
+__global__ void __launch_bounds__(kAdofThreads, COMPACT ? PPK_ADOF_MINB : 6)
 adof_step_kernel(const __grid_constant__ KArgs k) {
   using L = AdofLayout<COMPACT>;
   extern __shared__ __align__(128) float smem[];

@@ -112,3 +112,30 @@ def test_first_layer_consumes_the_task_step_output():
     ref.running_mean, ref.running_var = rms.running_mean.cpu(), rms.running_var.cpu()
     want = P.first_layer(ref.normalize(task.obs_buf.cpu()), w, b, "elu")
     assert_fp16_close(got, want, "task step -> first layer", ulps=2)
+
+
+def test_sharded_moments_merge_equals_single_update():
+    """Data-parallel form: every rank accumulates the moments of its shard, the moments and the row count are
+    summed across ranks (what all_reduce(SUM) does), every rank merges the global batch.  Emulated on one GPU
+    with two shards of unequal size; equals the single-rank update on the concatenated batch."""
+    import ctypes as C
+    from isaacgym_b200 import _native as N
+    lib = N.load()
+    x = batch(5000, 80, 21).to(DEV)
+    shards = [x[:1800].contiguous(), x[1800:].contiguous()]
+    single = RunningMeanStd(80, device=DEV)
+    single.update(batch(700, 80, 20).to(DEV))             # non-trivial prior state
+    ranks = [RunningMeanStd(80, device=DEV) for _ in shards]
+    for r in ranks:
+        r.running_mean.copy_(single.running_mean); r.running_var.copy_(single.running_var); r.count.copy_(single.count)
+    single.update(x)
+    for r, sh in zip(ranks, shards):
+        N.check(lib.ppk_rms_accumulate(r._struct(), sh.data_ptr(), sh.shape[0], N.current_stream_ptr()))
+    total = ranks[0]._moments[:160] + ranks[1]._moments[:160]          # the all-reduce
+    for r in ranks:
+        r._moments[:160].copy_(total)
+        N.check(lib.ppk_rms_merge(r._struct(), float(x.shape[0]), N.current_stream_ptr()))
+        torch.testing.assert_close(r.running_mean, single.running_mean, rtol=1e-12, atol=1e-12)
+        torch.testing.assert_close(r.running_var, single.running_var, rtol=1e-11, atol=1e-12)
+        assert float(r.count) == float(single.count)
+        assert float(r._moments.abs().sum()) == 0.0                   # cleared for the next batch
