@@ -285,7 +285,7 @@ typedef enum PpkActivation { PPK_ACT_NONE = 0, PPK_ACT_ELU = 1 } PpkActivation;
 
 /* The first nn.Linear(width -> units) of the actor (and, with `separate: True`, critic) MLP, packed
  * once at init into fp16 tensor-core operand tiles (the bias rides in the K padding).  units % 256 == 0;
- * width <= 95. */
+ * width <= 31, 64..95 or 304..319 (the observation widths of the task variants: 24, 80, 94, 313). */
 PPK_API size_t ppk_linear_packed_bytes(int32_t units, int32_t width);
 PPK_API int ppk_linear_pack(const float* weight /*[units,width]*/, const float* bias /*[units] or NULL*/, int32_t units,
                             int32_t width, void* packed, size_t packed_bytes, void* stream);

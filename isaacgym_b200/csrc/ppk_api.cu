@@ -465,16 +465,17 @@ int make_out_map(CUtensorMap* m, void* out, long long rows, int units) {
              : PPK_ERR_CUDA;
 }
 
-template <int KP>
+template <int KP, int KBLK>
 int launch_first_layer(const FlArgs& k, cudaStream_t s) {
+  using L = FlLayout<KP, KBLK>;
   CUtensorMap out_map;
   int rc = make_out_map(&out_map, k.out, k.rows, k.units);
   if (rc != PPK_OK) return rc;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(first_layer_kernel<KP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlLayout<KP>::kBytes) !=
+    if (cudaFuncSetAttribute(first_layer_kernel<KP, KBLK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes) !=
             cudaSuccess ||
-        cudaFuncSetAttribute(first_layer_kernel<KP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlLayout<KP>::kBytes) !=
+        cudaFuncSetAttribute(first_layer_kernel<KP, KBLK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes) !=
             cudaSuccess) {
       cudaGetLastError();
       return PPK_ERR_LAUNCH;
@@ -483,8 +484,8 @@ int launch_first_layer(const FlArgs& k, cudaStream_t s) {
   }
   const long long units = ((k.rows + kFlM - 1) / kFlM) * (k.units / kFlN);
   const unsigned grid = (unsigned)(units < 148 ? units : 148);      // persistent: one CTA per SM
-  if (k.activation == PPK_ACT_ELU) first_layer_kernel<KP, 1><<<grid, kFlThreads, FlLayout<KP>::kBytes, s>>>(k, out_map);
-  else first_layer_kernel<KP, 0><<<grid, kFlThreads, FlLayout<KP>::kBytes, s>>>(k, out_map);
+  if (k.activation == PPK_ACT_ELU) first_layer_kernel<KP, KBLK, 1><<<grid, kFlThreads, L::kBytes, s>>>(k, out_map);
+  else first_layer_kernel<KP, KBLK, 0><<<grid, kFlThreads, L::kBytes, s>>>(k, out_map);
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 }  // namespace
@@ -512,10 +513,11 @@ int ppk_policy_first_layer(const PpkRunningMeanStd* rms, const float* obs, int64
   k.out = static_cast<__half*>(out_f16);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (kp) {
-    case 32: return launch_first_layer<32>(k, s);
-    case 80: return launch_first_layer<80>(k, s);
-    case 96: return launch_first_layer<96>(k, s);
-    default: return PPK_ERR_SHAPE;     // wider inputs (ADOF: 313) need a K loop over operand stages
+    case 32: return launch_first_layer<32, 32>(k, s);
+    case 80: return launch_first_layer<80, 80>(k, s);
+    case 96: return launch_first_layer<96, 96>(k, s);       // TILT / NES / A3 / ALIGN (80) and A4 (94)
+    case 320: return launch_first_layer<320, 64>(k, s);     // ADOF (313): weights streamed in K blocks of 64
+    default: return PPK_ERR_SHAPE;
   }
 }
 

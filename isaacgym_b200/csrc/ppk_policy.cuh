@@ -177,16 +177,21 @@ static_assert(kFlStageRow == 128, "the output staging tile is laid out for the 1
 // constant 1 and column `width` of the weights is the bias, so the bias add happens inside the MMA (fp32
 // accumulation either way) instead of costing the epilogue an add and a load per element.
 __host__ __device__ constexpr int fl_kpad(int width) { return (width + 1 + 15) / 16 * 16; }
-__host__ __device__ constexpr size_t fl_chunk_bytes(int kp) { return (size_t)(kp / 8) * kFlBLbo; }
+// Inputs up to 95 columns keep the whole K of a weight chunk in one ring stage and two row-tile buffers.  Wider
+// inputs (ADOF: 313 -> KP = 320) stream the weights in K blocks of 64 and keep ONE row-tile buffer (82 KB).
+__host__ __device__ constexpr int fl_kblk(int kp) { return kp <= 96 ? kp : 64; }
 
-template <int KP>
+template <int KP, int KBLK>
 struct FlLayout {
+  static_assert(KP % KBLK == 0 && KBLK % 16 == 0, "K blocking");
   static constexpr int kKc = KP / 8;
+  static constexpr int kNkb = KP / KBLK;                               // K blocks per unit
+  static constexpr int kABufs = (KP == KBLK) ? 2 : 1;
   static constexpr int kABytes = kKc * kFlALbo;
-  static constexpr int kBBytes = kKc * kFlBLbo;
+  static constexpr int kBBytes = (KBLK / 8) * kFlBLbo;                 // one ring stage = one K block of a chunk
   static constexpr int kOffStage = 0;                                  // 1024-byte aligned tiles for the swizzle
   static constexpr int kOffA = 32 * kFlEpiWarps * kFlStageRow;
-  static constexpr int kOffB = kOffA + 2 * kABytes;
+  static constexpr int kOffB = kOffA + kABufs * kABytes;
   static constexpr int kOffCst = kOffB + 2 * kBBytes;
   static constexpr int kOffBar = kOffCst + 3 * KP * 4;      // mean, den, 1/den per column
   static constexpr int kBytes = kOffBar + 12 * 8 + 16;
@@ -194,7 +199,8 @@ struct FlLayout {
   static_assert(kBytes <= 227 * 1024, "shared memory budget");
 };
 
-// packed weight blob: [units/256 chunks][KP/8][256][8] fp16; column `width` holds the bias, the rest of the pad is 0
+// packed weight blob: [units/256 chunks][K blocks][KBLK/8][256][8] fp16 (one contiguous ring stage per chunk and K
+// block); column `width` holds the bias, the rest of the pad is 0
 __global__ void linear_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias, int units, int width, int kp,
                                    __half* __restrict__ packed) {
   const long long total = (long long)units * kp;
@@ -203,8 +209,8 @@ __global__ void linear_pack_kernel(const float* __restrict__ w, const float* __r
     const int j = (int)(i & 7);
     const long long t = i >> 3;
     const int nl = (int)(t % kFlN);
-    const long long t2 = t / kFlN;
-    const int kc = (int)(t2 % (kp / 8));
+    const long long t2 = t / kFlN;                 // = (chunk * nkb + kb) * (kblk / 8) + kc_local, and kb * (kblk / 8) + kc_local
+    const int kc = (int)(t2 % (kp / 8));           //   is the global 16-byte K piece: the blocked order IS the plain order
     const int chunk = (int)(t2 / (kp / 8));
     const int n = chunk * kFlN + nl, k = kc * 8 + j;
     float v = 0.0f;
@@ -319,10 +325,11 @@ __device__ __forceinline__ void fl_prep_tile(const FlArgs& k, const float* cst, 
   }
 }
 
-template <int KP, int ACT>
+template <int KP, int KBLK, int ACT>
 __global__ void __launch_bounds__(kFlThreads, 1)
 first_layer_kernel(const __grid_constant__ FlArgs k, const __grid_constant__ CUtensorMap out_map) {
-  using L = FlLayout<KP>;
+  using L = FlLayout<KP, KBLK>;
+  constexpr int NKB = L::kNkb, ABUFS = L::kABufs;
   extern __shared__ __align__(1024) unsigned char fl_smem[];
   unsigned char* a_s = fl_smem + L::kOffA;
   unsigned char* b_s = fl_smem + L::kOffB;
@@ -368,16 +375,18 @@ first_layer_kernel(const __grid_constant__ FlArgs k, const __grid_constant__ CUt
   __syncthreads();
 
   if (warp == 0) {
-    // ===== weight-chunk producer: one bulk copy per unit into the 2-deep ring =====
+    // ===== weight producer: one bulk copy per unit and K block into the 2-deep ring =====
     if (lane == 0) {
       for (long long u = u_begin; u < u_end; ++u) {
-        const long long it = u - u_begin;
-        const int s = (int)(it & 1), ph = (int)((it >> 1) & 1);
         const int nc = (int)(u % NC);
-        mbar_wait_relaxed(b_empty + s, ph ^ 1);
-        if (PPK_FL_DBG & 16) { tc::mbar_arrive(b_full + s); continue; }
-        mbar_arrive_expect_tx(b_full + s, (uint32_t)L::kBBytes);
-        bulk_g2s(b_s + s * L::kBBytes, k.packed + (size_t)nc * L::kBBytes, (uint32_t)L::kBBytes, b_full + s);
+        for (int kb = 0; kb < NKB; ++kb) {
+          const long long bi = (u - u_begin) * NKB + kb;
+          const int s = (int)(bi & 1), ph = (int)((bi >> 1) & 1);
+          mbar_wait_relaxed(b_empty + s, ph ^ 1);
+          if (PPK_FL_DBG & 16) { tc::mbar_arrive(b_full + s); continue; }
+          mbar_arrive_expect_tx(b_full + s, (uint32_t)L::kBBytes);
+          bulk_g2s(b_s + s * L::kBBytes, k.packed + ((size_t)nc * NKB + kb) * L::kBBytes, (uint32_t)L::kBBytes, b_full + s);
+        }
       }
     }
   } else if (warp == 1) {
@@ -390,17 +399,22 @@ first_layer_kernel(const __grid_constant__ FlArgs k, const __grid_constant__ CUt
         const long long mt = u / NC;
         const int nc = (int)(u - mt * NC);
         const long long j = mt - mt_begin;
-        const int ab = (int)(j & 1), aph = (int)((j >> 1) & 1);
+        const int ab = (int)(j % ABUFS), aph = (int)((j / ABUFS) & 1);
         if (it == 0 || nc == 0) mbar_wait(a_full + ab, aph);
-        mbar_wait(b_full + s, ph);
         mbar_wait(acc_empty + s, ph ^ 1);
-        tc::fence_after_sync();
-        const uint32_t a0 = smem_u32(a_s + ab * L::kABytes), b0 = smem_u32(b_s + s * L::kBBytes);
+        const uint32_t a0 = smem_u32(a_s + ab * L::kABytes);
+        for (int kb = 0; kb < NKB; ++kb) {
+          const long long bi = it * NKB + kb;
+          const int sb = (int)(bi & 1), phb = (int)((bi >> 1) & 1);
+          mbar_wait(b_full + sb, phb);
+          tc::fence_after_sync();
+          const uint32_t b0 = smem_u32(b_s + sb * L::kBBytes);
 #pragma unroll
-        for (int kk = 0; kk < ((PPK_FL_DBG & 4) ? 0 : KP / 16); ++kk)
-          tc::mma_f16(tmem_base + s * kFlN, tc::smem_desc(a0 + kk * 2 * kFlALbo, kFlALbo, 128),
-                      tc::smem_desc(b0 + kk * 2 * kFlBLbo, kFlBLbo, 128), idesc, kk > 0);
-        tc::mma_commit(b_empty + s);
+          for (int kk = 0; kk < ((PPK_FL_DBG & 4) ? 0 : KBLK / 16); ++kk)
+            tc::mma_f16(tmem_base + s * kFlN, tc::smem_desc(a0 + (kb * (KBLK / 16) + kk) * 2 * kFlALbo, kFlALbo, 128),
+                        tc::smem_desc(b0 + kk * 2 * kFlBLbo, kFlBLbo, 128), idesc, (kb | kk) > 0);
+          tc::mma_commit(b_empty + sb);
+        }
         if (u == u_end - 1 || nc == NC - 1) tc::mma_commit(a_empty + ab);
         tc::mma_commit(acc_full + s);
         FL_STAMP(it == 0, 3);
@@ -413,7 +427,7 @@ first_layer_kernel(const __grid_constant__ FlArgs k, const __grid_constant__ CUt
     const long long mt_last = (u_end - 1) / NC;
     for (long long mt = mt_begin; mt <= mt_last; ++mt) {
       const long long j = mt - mt_begin;
-      const int ab = (int)(j & 1), aph = (int)((j >> 1) & 1);
+      const int ab = (int)(j % ABUFS), aph = (int)((j / ABUFS) & 1);
       if (mt < mt_last) {               // pull the tile after this one into L2 while this one is worked on
         const long long r0 = (mt + 1) * kFlM;
         const long long bytes = (min((long long)kFlM, k.rows - r0)) * k.width * 4;

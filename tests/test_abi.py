@@ -111,7 +111,7 @@ def test_learner_side_argument_validation(lib):
     rms.struct_size = 8
     assert lib.ppk_rms_normalize(rms, 0x1000, 16, 0x1000, None) == -6             # PPK_ERR_ABI
     assert lib.ppk_policy_first_layer(None, 0x1000, 16, 80, 0x1000, 1000, 1, 0x1000, None) == -2   # units
-    assert lib.ppk_policy_first_layer(None, 0x1000, 16, 313, 0x1000, 2048, 1, 0x1000, None) == -2  # width > 95
+    assert lib.ppk_policy_first_layer(None, 0x1000, 16, 200, 0x1000, 2048, 1, 0x1000, None) == -2  # width without a tiling
     assert lib.ppk_policy_first_layer(None, 0x1000, 16, 80, 0x1000, 2048, 7, 0x1000, None) == -4   # activation
     assert lib.ppk_policy_first_layer(None, None, 16, 80, 0x1000, 2048, 1, 0x1000, None) == -1
     assert lib.ppk_policy_first_layer(None, 0x1000, 0, 80, 0x1000, 2048, 1, 0x1000, None) == 0     # empty batch

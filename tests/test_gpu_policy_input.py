@@ -63,7 +63,7 @@ def assert_fp16_close(got, want, ctx, ulps=1):
 
 
 @pytest.mark.parametrize("rows,width,units", [(4096, 80, 2048), (1000, 80, 512), (129, 94, 256), (5, 24, 256),
-                                              (20000, 80, 4096)])
+                                              (20000, 80, 4096), (3000, 313, 1024), (700, 313, 256)])
 @pytest.mark.parametrize("act", ["elu", "None"])
 def test_first_layer_matches_autocast_restatement(rows, width, units, act):
     g = torch.Generator().manual_seed(rows + width)
