@@ -7,12 +7,13 @@
 //   `mixed_precision: True` (yaml:50): fp16 operands, fp32 accumulation, fp16 result, ELU on the fp16 tensor.
 //
 // Kernels:
-//   rms_moments_kernel   per-column sum / sum of squares of a batch, fp64, HBM-bound streaming reduction
-//   rms_merge_kernel     batch moments -> running statistics (one CTA)
+//   rms_moments_kernel   per-column sum / sum of squares of a batch, fp64, HBM-bound streaming reduction; the
+//                        last CTA merges the batch into the running statistics (one launch per update)
+//   rms_merge_kernel     stand-alone merge (after data-parallel ranks all-reduced the moments)
 //   rms_apply_kernel     stand-alone normalisation, fp32 out
-//   linear_pack_kernel   nn.Linear weight [units, width] fp32 -> fp16 tensor-core operand tiles (once, at init)
-//   first_layer_kernel   obs -> clamp -> normalise -> fp16 -> tcgen05.mma (fp32 accumulators in TMEM)
-//                        -> + bias -> fp16 -> ELU -> fp16 rows, written with bulk stores.  The only GEMM on
+//   linear_pack_kernel   nn.Linear weight [units, width] (+ bias) fp32 -> fp16 tensor-core operand tiles (at init)
+//   first_layer_kernel   obs -> clamp -> normalise -> fp16 -> tcgen05.mma (fp32 accumulators in TMEM, bias inside
+//                        the K padding) -> fp16 -> ELU -> fp16 tiles -> TMA tensor stores.  The only GEMM on
 //                        either side of the path; bound by the [rows, units] fp16 write, not by the math.
 #pragma once
 #include <cuda.h>
@@ -444,7 +445,7 @@ first_layer_kernel(const __grid_constant__ FlArgs k, const __grid_constant__ CUt
       FL_STAMP(t == 0 && j == 1, 2);
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> + bias -> fp16 -> activation -> fp16 row piece -> bulk store =====
+    // ===== epilogue: TMEM -> registers -> fp16 -> activation -> fp16 -> swizzled warp tile -> tensor store =====
     const int ew = warp - (2 + kFlPrepWarps);
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int cq = ew >> 2;                 // which kFlEpiCols-wide slice of the chunk

@@ -1,7 +1,7 @@
 // 5th-generation tensor core plumbing for sm_100a: tensor memory (TMEM) allocation, shared-memory
 // matrix descriptors, the single-thread tcgen05.mma issue, commit-to-mbarrier and the TMEM -> register
-// load of the epilogue.  Only what ppk_policy.cuh needs (dense fp16 x fp16 -> fp32, one CTA per MMA,
-// K-major operands without swizzle).
+// load of the epilogue, tensor-map stores.  Only what ppk_policy.cuh needs (dense fp16 x fp16 -> fp32, one
+// CTA per MMA, K-major operands without swizzle).
 #pragma once
 #include <cstdint>
 
@@ -79,11 +79,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// 1-D bulk store shared -> global (TMA engine), tracked by the thread's bulk async-group
-__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
-               : "memory");
-}
 // 2-D tensor store shared -> global through a tensor map (TMA); rows / columns outside the tensor are clipped
 __device__ __forceinline__ void tensor_store_2d(const void* tmap, int c0, int c1, const void* ssrc) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1),
