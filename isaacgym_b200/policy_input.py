@@ -63,9 +63,10 @@ class RunningMeanStd:
                 or x.shape[1] != self.insize:
             raise ValueError(f"expected a contiguous float32 [rows,{self.insize}] tensor on {self.device}")
 
-    def update(self, x: torch.Tensor, group=None):
-        """Merge the batch moments.  With a process group the moments and the row count are all-reduced
-        first, so every rank ends with the statistics of the global batch."""
+    def update(self, x: torch.Tensor, group=None, global_rows: Optional[int] = None):
+        """Merge the batch moments.  With a process group the moments are all-reduced first, so every rank ends
+        with the statistics of the global batch; `global_rows` (the batch size summed over ranks, known to the
+        caller when the shards are equal) avoids all-reducing the row count and reading it back."""
         self._check(x)
         s = self._struct()
         if group is None:
@@ -73,10 +74,12 @@ class RunningMeanStd:
             return
         import torch.distributed as dist
         N.check(self._lib.ppk_rms_accumulate(s, x.data_ptr(), x.shape[0], N.current_stream_ptr()), "rms_accumulate")
-        rows = torch.tensor([float(x.shape[0])], dtype=torch.float64, device=self.device)
         dist.all_reduce(self._moments[:2 * self.insize], group=group)
-        dist.all_reduce(rows, group=group)
-        N.check(self._lib.ppk_rms_merge(s, float(rows.item()), N.current_stream_ptr()), "rms_merge")
+        if global_rows is None:
+            rows = torch.tensor([float(x.shape[0])], dtype=torch.float64, device=self.device)
+            dist.all_reduce(rows, group=group)
+            global_rows = rows.item()              # host read: pass global_rows to stay asynchronous
+        N.check(self._lib.ppk_rms_merge(s, float(global_rows), N.current_stream_ptr()), "rms_merge")
 
     def normalize(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         self._check(x)
