@@ -8,7 +8,7 @@ namespace ppk {
 // post_physics_step order BASE:587-596: progress += 1 -> reset_idx(envs whose reset_buf is set)
 // -> compute_observations -> compute_reward.  No rotation: the obs row is a gather of pos/vel of
 // paddle1, paddle2, ball1, ball2 (BASE:776-813).
-constexpr int kBaseWarps = 4;
+constexpr int kBaseWarps = 1;          // 4096 envs = 128 warps: one per CTA spreads them over the SMs
 constexpr int kBaseObs = 24;
 
 __global__ void __launch_bounds__(kBaseWarps * 32)
@@ -25,25 +25,8 @@ base_step_kernel(const __grid_constant__ KArgs k) {
 
   long long prog = k.progress[env] + ((phases & PPK_PHASE_PROGRESS) ? 1 : 0);
   float* gr = k.root + (size_t)env * rootN;
-  // reset_idx of the envs flagged by the PREVIOUS step's reward (BASE:589-591)
-  const bool base_resets = (phases & PPK_PHASE_RESET) && on && k.reset[env] != 0;
-  if (phases & PPK_PHASE_RESET) append_reset_indices(k, base_resets, env, lane);
-  if (k.timeout != nullptr && on) k.timeout[env] = (prog >= k.max_len - 1) ? 1 : 0;
-  if (base_resets) {
-    const float* ir = k.init_root + (size_t)env * rootN;
-    for (int a = 0; a < k.A; ++a)
-      for (int c = 0; c < 7; ++c) gr[a * kRow + c] = ir[a * kRow + c];     // velocities are NOT zeroed (BASE:533-534)
-    for (int c = 0; c < 3; ++c) {
-      gr[k.ball * kRow + 7 + c] = k.reset_vel[c];              // ball1 <- velocity_1 (BASE:549)
-      gr[(k.ball + 1) * kRow + 7 + c] = k.reset_vel[3 + c];    // ball2 <- velocity_2 (BASE:550)
-    }
-    const float* id = k.init_dof + (size_t)env * 2 * k.D;
-    float* gd = k.dof + (size_t)env * 2 * k.D;
-    for (int i = 0; i < 2 * k.D; ++i) gd[i] = id[i];
-    prog = 0;
-  }
-  if (on && (phases & (PPK_PHASE_PROGRESS | PPK_PHASE_RESET))) k.progress[env] = prog;
-
+  // every load the observation needs is requested up front, in one DRAM round trip with progress / reset;
+  // lanes whose env is reset below re-read their two ball rows afterwards (cache hits)
   const float* p1 = k.rb + ((size_t)env * k.B + k.paddle_body[0]) * kRow;
   const float* p2 = k.rb + ((size_t)env * k.B + k.paddle_body[1]) * kRow;
   const float* b1 = gr + k.ball * kRow;
@@ -55,6 +38,37 @@ base_step_kernel(const __grid_constant__ KArgs k) {
     o[6 + c] = p2[c]; o[9 + c] = p2[7 + c];
     o[12 + c] = b1[c]; o[15 + c] = b1[7 + c];
     o[18 + c] = b2[c]; o[21 + c] = b2[7 + c];
+  }
+  // reset_idx of the envs flagged by the PREVIOUS step's reward (BASE:589-591)
+  const bool base_resets = (phases & PPK_PHASE_RESET) && on && k.reset[env] != 0;
+  if (phases & PPK_PHASE_RESET) append_reset_indices(k, base_resets, env, lane);
+  if (k.timeout != nullptr && on) k.timeout[env] = (prog >= k.max_len - 1) ? 1 : 0;
+  // the warp resets its flagged envs one after the other, all lanes copying (coalesced rows instead of one
+  // lane walking 35 + 2*52 floats)
+  for (unsigned pending = __ballot_sync(0xffffffffu, base_resets); pending != 0; pending &= pending - 1) {
+    const long long e = env0 + (__ffs(pending) - 1);
+    const float* ir = k.init_root + (size_t)e * rootN;
+    float* ge = k.root + (size_t)e * rootN;
+    for (int f = lane; f < k.A * 7; f += 32) {              // pos + rot; velocities are NOT zeroed (BASE:533-534)
+      const int a = f / 7, c = f - a * 7;
+      ge[a * kRow + c] = ir[a * kRow + c];
+    }
+    if (lane < 6)                                           // ball1 <- velocity_1, ball2 <- velocity_2 (BASE:549-550)
+      ge[(k.ball + lane / 3) * kRow + 7 + lane % 3] = k.reset_vel[lane];
+    const float* id = k.init_dof + (size_t)e * 2 * k.D;
+    float* gd = k.dof + (size_t)e * 2 * k.D;
+    for (int i = lane; i < 2 * k.D; i += 32) gd[i] = id[i];
+  }
+  __syncwarp();                                             // the observations below read the rows just written
+  if (base_resets) prog = 0;
+  if (on && (phases & (PPK_PHASE_PROGRESS | PPK_PHASE_RESET))) k.progress[env] = prog;
+
+  if (base_resets) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o[12 + c] = b1[c]; o[15 + c] = b1[7 + c];
+      o[18 + c] = b2[c]; o[21 + c] = b2[7 + c];
+    }
   }
   if (phases & PPK_PHASE_OBS) {
 #pragma unroll
