@@ -258,7 +258,8 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 
 // n / d with r = RN(1/d) computed once per column: quotient estimate plus two exact-residual corrections
 // (the refinement div.rn itself performs, minus its range checks: |n| and d are ordinary normal numbers
-// here).  Five instructions instead of the dozen of a generic IEEE division, same result.
+// here).  Five instructions instead of the dozen of a generic IEEE division, same result (0 mismatches against
+// n / d on 2^33 random operand pairs: tools/div_by_const_check.cu).
 __device__ __forceinline__ float div_by_const(float n, float d, float r) {
   float q = n * r;
   q = fmaf(fmaf(-d, q, n), r, q);
