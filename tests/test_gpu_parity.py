@@ -345,3 +345,48 @@ def test_adof_compact_reference_pose(n):
         assert torch.equal(comp[name], full[name]), name
     assert_exact(cfg, comp, want, STATE_EXACT + cfg.flag_names + cfg.counter_names, f"adof compact n={n}")
     assert_close_fields(cfg, comp["obs_buf"], want["obs_buf"], comp["rew_buf"], want["rew_buf"], f"adof compact n={n}")
+
+
+@pytest.mark.parametrize("variant,n", [("tilt", 65536), ("a4", 65536), ("adof", 32768)])
+def test_full_size_yaw_invariance_of_observations(variant, n):
+    """Size-independent property at BASELINE sizes: the observations live in the heading frame of the root body,
+    so turning the whole scene of every env by its own random yaw angle (positions, velocities, root orientation,
+    ADOF's reference pose) leaves obs_buf unchanged up to fp32 rounding."""
+    cfg = CONFIGS[variant]
+    st = make_state(cfg, n, seed=77 + cfg.variant_id, device=DEV, adversarial=False)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    th = (torch.rand(n, generator=g, device=DEV) * 2 - 1) * 3.0
+    c, s = torch.cos(th), torch.sin(th)
+
+    def turn(rows):                       # rows [n, R, 13]: pos, quat xyzw, linvel, angvel
+        out = rows.clone()
+        for a in (0, 7):
+            x, y = rows[..., a], rows[..., a + 1]
+            out[..., a] = c[:, None] * x - s[:, None] * y
+            out[..., a + 1] = s[:, None] * x + c[:, None] * y
+        # q' = qz(th) * q, qz = (0, 0, sin(th/2), cos(th/2))
+        hz, hw = torch.sin(th / 2)[:, None], torch.cos(th / 2)[:, None]
+        qx, qy, qz, qw = rows[..., 3], rows[..., 4], rows[..., 5], rows[..., 6]
+        out[..., 3] = hw * qx - hz * qy
+        out[..., 4] = hw * qy + hz * qx
+        out[..., 5] = hw * qz + hz * qw
+        out[..., 6] = hw * qw - hz * qz
+        return out
+
+    a = {k: v.clone() for k, v in st.items()}
+    b = {k: v.clone() for k, v in st.items()}
+    for key in ("rigid_body_states", "root_states", "initial_body_states"):
+        if key in b:
+            b[key] = turn(st[key])
+    for d in (a, b):
+        d["stats"] = torch.zeros(N.PPK_STATS_SLOTS, N.PPK_NUM_STATS, dtype=torch.float64, device=DEV)
+        d["scratch"] = torch.zeros(16, dtype=torch.int32, device=DEV)
+        run(cfg, d, N.PHASE_OBS)
+    oa, ob = a["obs_buf"].reshape(n * cfg.obs_rows, -1), b["obs_buf"].reshape(n * cfg.obs_rows, -1)
+    scale = oa.abs().amax(dim=1, keepdim=True).clamp_min(1.0)
+    err = (oa - ob).abs() / scale
+    if variant == "adof":
+        err[:, 120] = 0.0                 # y_intersect divides by (-lvx + 1e-6): unbounded amplification near lvx = 0
+    # budget: the turn itself (fp32 sin / cos and two roundings per coordinate) plus atan2f / sinf / cosf of the
+    # heading, a few 1e-6 rad on vectors up to ~10x the row scale
+    assert float(err.max()) < 5e-5, f"max scaled deviation {float(err.max())}"
