@@ -139,3 +139,29 @@ def test_sharded_moments_merge_equals_single_update():
         torch.testing.assert_close(r.running_var, single.running_var, rtol=1e-11, atol=1e-12)
         assert float(r.count) == float(single.count)
         assert float(r._moments.abs().sum()) == 0.0                   # cleared for the next batch
+
+
+def test_first_layer_full_size_properties():
+    """65 536 x 80 -> 2048 (the TILT batch): deterministic, every output row depends on its input row only (a slice
+    of the batch run on its own gives bit-identical rows, whatever tile it lands in), and a random sample of rows
+    matches the oracle."""
+    rows, width, units = 65536, 80, 2048
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(rows, width, device=DEV, generator=g) * 2 + 0.3
+    w = torch.randn(units, width, device=DEV, generator=g) / width ** 0.5
+    b = torch.randn(units, device=DEV, generator=g) * 0.1
+    rms = RunningMeanStd(width, device=DEV)
+    rms.update(x)
+    rms.eval()
+    layer = FirstLayer(w, b, "elu", rms)
+    full = layer(x)
+    again = layer(x)
+    assert torch.equal(full, again)
+    for lo, hi in ((0, 1000), (12345, 13345), (65536 - 77, 65536)):
+        part = layer(x[lo:hi].contiguous())
+        assert torch.equal(part, full[lo:hi]), f"rows {lo}:{hi} depend on their position in the batch"
+    idx = torch.randint(0, rows, (1500,), generator=torch.Generator().manual_seed(1))
+    ref = P.RunningMeanStd(width)
+    ref.running_mean, ref.running_var = rms.running_mean.cpu(), rms.running_var.cpu()
+    want = P.first_layer(ref.normalize(x[idx.to(DEV)].cpu()), w.cpu(), b.cpu(), "elu")
+    assert_fp16_close(full[idx.to(DEV)], want, "full-size sample", ulps=2)
