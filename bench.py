@@ -133,9 +133,7 @@ def run_learner_side(tasks, units, peak, iters=40, warm=5):
     x 2 B) is larger than L2 by itself."""
     import torch
     from isaacgym_b200.policy_input import FirstLayer, RunningMeanStd
-    obs = [t.obs_buf.view(t.obs_buf.shape[0], -1) if t.obs_buf.dim() == 2 else None for t in tasks]
-    if any(o is None for o in obs):
-        return {"skipped": "obs_buf is not [N, num_obs]"}
+    obs = [t.obs_buf.view(-1, t.obs_buf.shape[-1]) for t in tasks]        # A4: one row per humanoid
     rows, width = obs[0].shape
     dev = obs[0].device
     g = torch.Generator(device=dev).manual_seed(0)
