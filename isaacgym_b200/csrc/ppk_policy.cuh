@@ -371,6 +371,17 @@ first_layer_kernel(const __grid_constant__ FlArgs k, const __grid_constant__ CUt
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   FL_STAMP(threadIdx.x == 0, 0);
+  // weight stage `bi` of this CTA's sequence (unit-major, K blocks inside a unit)
+  auto load_weights = [&](long long bi) {
+    const long long u = u_begin + bi / NKB;
+    const int kb = (int)(bi % NKB), nc = (int)(u % NC), s = (int)(bi & 1);
+    mbar_arrive_expect_tx(b_full + s, (uint32_t)L::kBBytes);
+    bulk_g2s(b_s + s * L::kBBytes, k.packed + ((size_t)nc * NKB + kb) * L::kBBytes, (uint32_t)L::kBBytes, b_full + s);
+  };
+  const long long n_stages = (u_end - u_begin) * NKB;
+  // both ring stages are requested before the first row tile is prepared, so the two latencies overlap
+  if (threadIdx.x == 0 && !(PPK_FL_DBG & 16))
+    for (long long bi = 0; bi < 2 && bi < n_stages; ++bi) load_weights(bi);
   // the CTA's first row tile is on the critical path of everything: all warps prepare it together
   fl_prep_tile<KP, 2>(k, cst, mt_begin, a_s, threadIdx.x, kFlThreads);
   tc::fence_proxy_async_smem();
@@ -379,16 +390,11 @@ first_layer_kernel(const __grid_constant__ FlArgs k, const __grid_constant__ CUt
   if (warp == 0) {
     // ===== weight producer: one bulk copy per unit and K block into the 2-deep ring =====
     if (lane == 0) {
-      for (long long u = u_begin; u < u_end; ++u) {
-        const int nc = (int)(u % NC);
-        for (int kb = 0; kb < NKB; ++kb) {
-          const long long bi = (u - u_begin) * NKB + kb;
-          const int s = (int)(bi & 1), ph = (int)((bi >> 1) & 1);
-          mbar_wait_relaxed(b_empty + s, ph ^ 1);
-          if (PPK_FL_DBG & 16) { tc::mbar_arrive(b_full + s); continue; }
-          mbar_arrive_expect_tx(b_full + s, (uint32_t)L::kBBytes);
-          bulk_g2s(b_s + s * L::kBBytes, k.packed + ((size_t)nc * NKB + kb) * L::kBBytes, (uint32_t)L::kBBytes, b_full + s);
-        }
+      for (long long bi = (PPK_FL_DBG & 16) ? 0 : 2; bi < n_stages; ++bi) {
+        const int s = (int)(bi & 1), ph = (int)((bi >> 1) & 1);
+        mbar_wait_relaxed(b_empty + s, ph ^ 1);
+        if (PPK_FL_DBG & 16) { tc::mbar_arrive(b_full + s); continue; }
+        load_weights(bi);
       }
     }
   } else if (warp == 1) {
