@@ -257,8 +257,9 @@ PPK_API int ppk_host_session_traffic(const PpkHostSession* s, int64_t* h2d_bytes
  * (rl_games/algos_torch/running_mean_std.py; un-vendored, restated in oracle/policy_oracle.py):
  * fp64 running_mean / running_var [width] and count [1], epsilon 1e-5, output clamped to +-5.
  * `clip_obs` is VecTask.step's clamp of obs_buf (clipObservations; <= 0 = none = upstream default inf).
- * `moments` is a caller-owned, zero-initialised fp64 scratch of 2*width + 1 entries (column sums and sums
- * of squares of the batches not yet merged, and a ticket word). */
+ * `moments` is a caller-owned, zero-initialised fp64 scratch of ppk_rms_scratch_doubles(width) entries: the
+ * first 2*width are the column sums and sums of squares of the batches not yet merged (what data-parallel
+ * ranks all-reduce), the rest is a ticket word and the copies of the accumulators the CTAs add into. */
 typedef struct PpkRunningMeanStd {
   uint32_t struct_size;
   int32_t width;
@@ -270,6 +271,7 @@ typedef struct PpkRunningMeanStd {
   double* moments;
 } PpkRunningMeanStd;
 
+PPK_API size_t ppk_rms_scratch_doubles(int32_t width);
 /* moments += (sum_r x, sum_r x^2) over obs [rows,width].  Data-parallel ranks all-reduce (SUM) `moments`
  * and the row count before merging, so that every rank holds the statistics of the global batch. */
 PPK_API int ppk_rms_accumulate(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, void* stream);

@@ -120,6 +120,8 @@ def load():
     lib.ppk_rms_update.argtypes = [rp, C.c_void_p, C.c_int64, C.c_void_p]
     lib.ppk_rms_normalize.restype = C.c_int
     lib.ppk_rms_normalize.argtypes = [rp, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.ppk_rms_scratch_doubles.restype = C.c_size_t
+    lib.ppk_rms_scratch_doubles.argtypes = [C.c_int32]
     lib.ppk_linear_packed_bytes.restype = C.c_size_t
     lib.ppk_linear_packed_bytes.argtypes = [C.c_int32, C.c_int32]
     lib.ppk_linear_pack.restype = C.c_int

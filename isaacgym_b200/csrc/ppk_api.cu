@@ -345,7 +345,7 @@ int rms_launch_moments(const PpkRunningMeanStd* rms, const RmsArgs& a, const flo
   if (R < 1) R = 1;
   if (R < (vec ? 8 : 2)) R = (wx * (vec ? 8 : 2) <= 1024) ? (vec ? 8 : 2) : R;     // the fold needs 2*VEC row slots
   long long blocks = (rows + (long long)R * 4 - 1) / ((long long)R * 4);
-  if (blocks > 148) blocks = 148;       // one CTA per SM: 2 fp64 atomics per column and CTA
+  if (blocks > kRmsMaxCtas) blocks = kRmsMaxCtas;   // one CTA per SM
   if (blocks < 1) blocks = 1;
   const size_t smem = sizeof(double) * 2 * (vec ? 4 : 1) * R * wx;
   if (vec) {
@@ -411,6 +411,11 @@ int ppk_rms_normalize(const PpkRunningMeanStd* rms, const float* obs, int64_t ro
   if (vec) rms_apply_kernel<4><<<(unsigned)blocks, dim3(wx, R), 0, s>>>(a, obs, rows, out);
   else rms_apply_kernel<1><<<(unsigned)blocks, dim3(wx, R), 0, s>>>(a, obs, rows, out);
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+
+size_t ppk_rms_scratch_doubles(int32_t width) {
+  if (width <= 0 || width > 512) return 0;
+  return (size_t)2 * width * (1 + kRmsSlots) + 1;
 }
 
 size_t ppk_linear_packed_bytes(int32_t units, int32_t width) {

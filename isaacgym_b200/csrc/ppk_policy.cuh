@@ -39,7 +39,7 @@ __device__ __forceinline__ float clamp_obs(float x, float clip) { return clip > 
 // RunningMeanStd._update_mean_var_count_from_moments for one column, batch mean / unbiased batch variance
 // from the fp64 sums; clears the sums for the next batch.
 __device__ __forceinline__ void rms_merge_column(const RmsArgs& a, double* sums, double batch_rows, double count, int c) {
-  const double S = __ldcg(sums + c), SS = __ldcg(sums + a.width + c);      // written by L2 atomics
+  const double S = sums[c], SS = sums[a.width + c];
   const double bmean = S / batch_rows;
   const double bvar = (SS - S * bmean) / (batch_rows - 1.0);   // torch.var: correction = 1 (nan for one row, as torch)
   const double delta = bmean - a.mean[c];
@@ -51,10 +51,16 @@ __device__ __forceinline__ void rms_merge_column(const RmsArgs& a, double* sums,
   sums[a.width + c] = 0.0;
 }
 
+constexpr int kRmsMaxCtas = 148;      // one CTA per SM
+constexpr int kRmsSlots = 8;          // copies of the 2W accumulators the CTAs' atomics are spread over
+
 // Column sums and sums of squares of obs [rows, width] in fp64.  VEC = 4: threadIdx.x owns four adjacent
-// columns (one 16-byte load per row), threadIdx.y walks the rows; four rows in flight per thread.
-// sums[0..W) += sum_r x, sums[W..2W) += sum_r x^2 (two fp64 atomics per column and CTA).  With merge != 0 the
-// last CTA to finish (ticket in sums[2W]) folds the batch into the running statistics: one launch per update.
+// columns (one 16-byte load per row), threadIdx.y walks the rows; eight rows in flight per thread.
+// Every CTA adds its 2W partial sums into one of kRmsSlots copies of the accumulators (same-address fp64
+// atomics serialise at ~50 ns each: 148 onto one address cost 7 us, 19 cost 1 us); the last CTA to finish
+// (ticket) folds the copies into sums[0..2W) (+=) and clears them; with merge != 0 it then folds the batch
+// into the running statistics: one launch per update.
+// scratch layout: [0,2W) sums | [2W] ticket | [2W+1 + slot*2W ...) accumulator copies
 template <int VEC>
 __global__ void rms_moments_kernel(RmsArgs a, const float* __restrict__ obs, long long rows, double* sums, int merge,
                                    double batch_rows) {
@@ -67,32 +73,33 @@ __global__ void rms_moments_kernel(RmsArgs a, const float* __restrict__ obs, lon
   for (int v = 0; v < VEC; ++v) s[v] = ss[v] = 0.0;
   if (on) {
     const long long step = (long long)gridDim.x * R;
-    long long r = (long long)blockIdx.x * R + ry;
-    constexpr int U = 4;
-    for (; r + (U - 1) * step < rows; r += U * step) {
+    constexpr int U = 8;
+    for (long long r0 = (long long)blockIdx.x * R + ry; r0 < rows; r0 += U * step) {
       float x[U][VEC];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const float* p = obs + (r + u * step) * width + cx * VEC;
-        if (VEC == 4) { const float4 t = __ldcs(reinterpret_cast<const float4*>(p)); x[u][0] = t.x; x[u][1] = t.y; x[u][2] = t.z; x[u][VEC - 1] = t.w; }
-        else x[u][0] = __ldcs(p);
+        const long long r = r0 + u * step;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) x[u][v] = 0.0f;
+        if (r < rows) {
+          const float* p = obs + r * width + cx * VEC;
+          if (VEC == 4) { const float4 t = __ldcs(reinterpret_cast<const float4*>(p)); x[u][0] = t.x; x[u][1] = t.y; x[u][2] = t.z; x[u][VEC - 1] = t.w; }
+          else x[u][0] = __ldcs(p);
+          if (a.clip > 0.0f) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) x[u][v] = clamp_obs(x[u][v], a.clip);
+          }
+        }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
+      for (int u = 0; u < U; ++u)         // rows past the end contribute exact zeros
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-          const double d = (double)clamp_obs(x[u][v], a.clip);
+          const double d = (double)x[u][v];
           s[v] += d;
           ss[v] += d * d;
         }
     }
-    for (; r < rows; r += step)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const double d = (double)clamp_obs(__ldcs(obs + r * width + cx * VEC + v), a.clip);
-        s[v] += d;
-        ss[v] += d * d;
-      }
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       red[((2 * v) * R + ry) * WX + cx] = s[v];
@@ -100,14 +107,14 @@ __global__ void rms_moments_kernel(RmsArgs a, const float* __restrict__ obs, lon
     }
   }
   __syncthreads();
-  // thread (cx, ry < 2*VEC) folds one of the 2*VEC partial arrays of column group cx
+  // thread (cx, ry < 2*VEC) folds one of the 2*VEC partial arrays of column group cx into the CTA's scratch row
+  double* slot = sums + 2 * width + 1 + (size_t)(blockIdx.x % kRmsSlots) * 2 * width;
   if (on && ry < 2 * VEC) {
     double t = 0.0;
     for (int y = 0; y < R; ++y) t += red[(ry * R + y) * WX + cx];
     const int v = ry >> 1;
-    atomicAdd(sums + ((ry & 1) ? width : 0) + cx * VEC + v, t);
+    atomicAdd(slot + ((ry & 1) ? width : 0) + cx * VEC + v, t);
   }
-  if (!merge) return;
   __shared__ unsigned int last;
   __threadfence();
   __syncthreads();
@@ -120,6 +127,19 @@ __global__ void rms_moments_kernel(RmsArgs a, const float* __restrict__ obs, lon
   if (!last) return;
   __threadfence();
   const double count = *a.count;
+  __syncthreads();
+  double* slots = sums + 2 * width + 1;
+  for (int c = ry * WX + cx; c < 2 * width; c += R * WX) {
+    double t[kRmsSlots];
+#pragma unroll
+    for (int b = 0; b < kRmsSlots; ++b) t[b] = __ldcg(slots + (size_t)b * 2 * width + c);     // written by L2 atomics
+    double tot = 0.0;
+#pragma unroll
+    for (int b = 0; b < kRmsSlots; ++b) { tot += t[b]; slots[(size_t)b * 2 * width + c] = 0.0; }
+    sums[c] += tot;
+  }
+  if (!merge) return;
+  __threadfence_block();
   __syncthreads();
   for (int c = ry * WX + cx; c < width; c += R * WX) rms_merge_column(a, sums, batch_rows, count, c);
   if (cx == 0 && ry == 0) *a.count = count + batch_rows;
@@ -145,15 +165,28 @@ __global__ void rms_apply_kernel(RmsArgs a, const float* __restrict__ obs, long 
     d[v] = sqrtf((float)a.var[cx * VEC + v] + a.eps);
   }
   const long long step = (long long)gridDim.x * R;
-  for (long long r = (long long)blockIdx.x * R + ry; r < rows; r += step) {
-    const long long off = r * a.width + cx * VEC;
-    float x[VEC];
-    if (VEC == 4) { const float4 t = __ldcs(reinterpret_cast<const float4*>(obs + off)); x[0] = t.x; x[1] = t.y; x[2] = t.z; x[VEC - 1] = t.w; }
-    else x[0] = __ldcs(obs + off);
+  constexpr int U = 4;                       // rows in flight per thread
+  for (long long r0 = (long long)blockIdx.x * R + ry; r0 < rows; r0 += U * step) {
+    float x[U][VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) x[v] = fminf(fmaxf((clamp_obs(x[v], a.clip) - m[v]) / d[v], -5.0f), 5.0f);
-    if (VEC == 4) __stcs(reinterpret_cast<float4*>(out + off), make_float4(x[0], x[1], x[2], x[VEC - 1]));
-    else __stcs(out + off, x[0]);
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * step;
+      if (r < rows) {
+        const long long off = r * a.width + cx * VEC;
+        if (VEC == 4) { const float4 t = __ldcs(reinterpret_cast<const float4*>(obs + off)); x[u][0] = t.x; x[u][1] = t.y; x[u][2] = t.z; x[u][VEC - 1] = t.w; }
+        else x[u][0] = __ldcs(obs + off);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * step;
+      if (r >= rows) break;
+      const long long off = r * a.width + cx * VEC;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) x[u][v] = fminf(fmaxf((clamp_obs(x[u][v], a.clip) - m[v]) / d[v], -5.0f), 5.0f);
+      if (VEC == 4) __stcs(reinterpret_cast<float4*>(out + off), make_float4(x[u][0], x[u][1], x[u][2], x[u][VEC - 1]));
+      else __stcs(out + off, x[u][0]);
+    }
   }
 }
 

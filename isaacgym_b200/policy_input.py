@@ -31,9 +31,9 @@ class RunningMeanStd:
         self.running_mean = torch.zeros(self.insize, dtype=torch.float64, device=self.device)
         self.running_var = torch.ones(self.insize, dtype=torch.float64, device=self.device)
         self.count = torch.ones((), dtype=torch.float64, device=self.device)
-        self._moments = torch.zeros(2 * self.insize + 1, dtype=torch.float64, device=self.device)
         self.training = True
         self._lib = N.load()
+        self._moments = torch.zeros(self._lib.ppk_rms_scratch_doubles(self.insize), dtype=torch.float64, device=self.device)
         self._s = self._make_struct()           # the buffers never move: build the descriptor once
 
     def train(self, mode: bool = True):
