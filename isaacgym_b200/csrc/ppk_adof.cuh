@@ -163,18 +163,17 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
     if (bulk) mbar_wait(bar, 0);
     const int bal_id = (lane < NB) ? k.bal_ids[lane] : k.bal_ids[0];
     const int bal_root = k.bal_ids[0];
-    // heading frames of this warp's envs, computed once with lane = pass slot and broadcast per pass
-    Heading my_hq; my_hq.sz = 0.0f; my_hq.cw = 1.0f;
-    {
-      const int e = (warp - 1) + kAdofObsWarps * lane;
-      if (e < T) {
-        const float* r0 = rb_s + e * L::kSRb + win_off(g_rb, e) + pp_root * kRow;
-        my_hq = heading_quat_inv(r0[3], r0[4], r0[5], r0[6]);
-      }
+    // heading frames of the tile's 8 envs: warp 1 computes them once (lane = env; atan2f / sinf / cosf are ~140
+    // instructions whatever the number of active lanes) and publishes them in hdr_s for the other obs warps
+    if (warp == 1 && lane < T) {
+      const float* r0 = rb_s + lane * L::kSRb + win_off(g_rb, lane) + pp_root * kRow;
+      const Heading hq = heading_quat_inv(r0[3], r0[4], r0[5], r0[6]);
+      float* hd = hdr_s + lane * L::kSHdr;
+      hd[H_A0] = 2.0f * (hq.cw * hq.cw) - 1.0f; hd[H_SZ] = hq.sz; hd[H_CW] = hq.cw;
     }
-    int slot = 0;
+    asm volatile("bar.sync 3, %0;" ::"n"(32 * kAdofObsWarps) : "memory");
 #pragma unroll 1
-    for (int e = warp - 1; e < T; e += kAdofObsWarps, ++slot) {
+    for (int e = warp - 1; e < T; e += kAdofObsWarps) {
       const float* rb_e = rb_s + e * L::kSRb + win_off(g_rb, e);
       const float* in_e = init_s + e * L::kSInit + win_off(g_init, e);
       const float* cur = rb_e + bal_id * kRow;
@@ -184,12 +183,12 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
       // imitation diffs: ref - cur (ADOF:1345,1349 / ADOF:1908-1909)
       float dpx = ref[0] - cur[0], dpy = ref[1] - cur[1], dpz = ref[2] - cur[2];
       float dvx = refv[0] - cur[7], dvy = refv[1] - cur[8], dvz = refv[2] - cur[9];
-      // has_fallen uses cur - ref (ADOF:1412)
-      float nx = cur[0] - ref[0], ny = cur[1] - ref[1], nz = cur[2] - ref[2];
       // per-body sums of squares; the /3 of the inner mean is applied once per env in phase R
       float s_dp2 = body_on ? (dpx * dpx + dpy * dpy + dpz * dpz) : 0.0f;
       float s_dv2 = body_on ? (dvx * dvx + dvy * dvy + dvz * dvz) : 0.0f;
-      float s_nrm = body_on ? sqrtf(nx * nx + ny * ny + nz * nz) : 0.0f;
+      // has_fallen uses the norm of cur - ref (ADOF:1412): cur - ref == -(ref - cur) exactly and squares drop
+      // the sign, so it is the square root of the same sum, bit for bit
+      float s_nrm = sqrtf(s_dp2);
       // DOF terms, lane = DOF index
       const bool dof_on = lane < D;
       const int dl = dof_on ? lane : 0;
@@ -204,19 +203,14 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
       const float red = warp_sum8(s_dp2, s_dv2, s_nrm, s_dq22, s_dq5, s_dqd22, s_pow, 0.0f, lane);
       // heading frames: ping-pong root body and balance root body (both row 0 in the shipped config)
       const float* r0 = rb_e + pp_root * kRow;
+      float* hd = hdr_s + e * L::kSHdr;
       Heading hq_pp;
-      hq_pp.sz = __shfl_sync(full, my_hq.sz, slot);
-      hq_pp.cw = __shfl_sync(full, my_hq.cw, slot);
+      hq_pp.sz = hd[H_SZ];
+      hq_pp.cw = hd[H_CW];
       const float* b0 = rb_e + bal_root * kRow;
       Heading hq_bal = (bal_root == pp_root) ? hq_pp : heading_quat_inv(b0[3], b0[4], b0[5], b0[6]);
-      {
-        float* hd = hdr_s + e * L::kSHdr;
-        if ((lane & 3) == 0 && lane < 28) hd[H_SUM_DP2 + (lane >> 2)] = red;     // slots are consecutive
-        if (lane == 31) {
-          hd[H_A0] = 2.0f * (hq_pp.cw * hq_pp.cw) - 1.0f; hd[H_SZ] = hq_pp.sz; hd[H_CW] = hq_pp.cw;
-          hd[H_RX] = r0[0]; hd[H_RY] = r0[1]; hd[H_RZ] = r0[2];
-        }
-      }
+      if ((lane & 3) == 0 && lane < 28) hd[H_SUM_DP2 + (lane >> 2)] = red;     // slots are consecutive
+      if (lane == 31) { hd[H_RX] = r0[0]; hd[H_RY] = r0[1]; hd[H_RZ] = r0[2]; }
       if ((phases & PPK_PHASE_OBS) && e < nvalid) {
         // ping-pong bodies [0,60), lane = output float o: body o/3, component o%3 (ADOF:1849-1888);
         //   out_c = v_c*a0 + ((s1*v_o)*m)*2 == my_quat_rotate((0,0,sz,cw), v) component by component
@@ -237,15 +231,19 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
         rotate_heading(hq_bal, dvx, dvy, dvz, lv[0], lv[1], lv[2]);
         lp[0] *= 10.0f; lp[1] *= 10.0f; lp[2] *= 10.0f;
         float* orow = g_obs + (size_t)e * kAdofObs + (6 * J + 2 * D + 7);
+        // [body][xyz] -> 69 consecutive floats: through shared memory.  This env's reference rows have been
+        // consumed (diffs are in registers), their staging area is the scratch; 18 shuffles + selects cost 3x more.
+        float* tr = init_s + e * L::kSInit;
+        __syncwarp();
+        if (body_on) {
+          tr[3 * lane] = lp[0]; tr[3 * lane + 1] = lp[1]; tr[3 * lane + 2] = lp[2];
+          tr[3 * NB + 3 * lane] = lv[0]; tr[3 * NB + 3 * lane + 1] = lv[1]; tr[3 * NB + 3 * lane + 2] = lv[2];
+        }
+        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int o = (body_on ? lane : 0) + i * NB;
-          const int src = o / 3, comp = o - src * 3;
-          float x = __shfl_sync(full, lp[0], src), y = __shfl_sync(full, lp[1], src), z = __shfl_sync(full, lp[2], src);
-          float pv = comp == 0 ? x : (comp == 1 ? y : z);
-          x = __shfl_sync(full, lv[0], src); y = __shfl_sync(full, lv[1], src); z = __shfl_sync(full, lv[2], src);
-          float vv = comp == 0 ? x : (comp == 1 ? y : z);
-          if (body_on) { st_stream(orow + o, pv); st_stream(orow + 3 * NB + o, vv); }
+        for (int o = lane; o < 3 * NB; o += 32) {
+          st_stream(orow + o, tr[o]);
+          st_stream(orow + 3 * NB + o, tr[3 * NB + o]);
         }
       }
     }
