@@ -458,17 +458,10 @@ inline int launch_adof(const KArgs& k0, cudaStream_t s) {
   for (const void* p : al) bulk = bulk && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
   k.bulk_ok = bulk ? 1 : 0;
   const size_t smem = (size_t)(compact ? AdofLayout<true>::kFloats : AdofLayout<false>::kFloats) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(adof_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(AdofLayout<false>::kFloats * sizeof(float))) != cudaSuccess ||
-        cudaFuncSetAttribute(adof_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(AdofLayout<true>::kFloats * sizeof(float))) != cudaSuccess) {
-      cudaGetLastError();
-      return PPK_ERR_LAUNCH;
-    }
-    configured = true;
-  }
+  static SmemOptIn opt_full, opt_compact;
+  if (!opt_full.ensure(adof_step_kernel<false>, AdofLayout<false>::kFloats * sizeof(float)) ||
+      !opt_compact.ensure(adof_step_kernel<true>, AdofLayout<true>::kFloats * sizeof(float)))
+    return PPK_ERR_LAUNCH;
   const bool fused_reset = (k.phases & PPK_PHASE_RESET) != 0 && !(k.phases & kPhaseDeferCounterClear);
   const long long tiles = (k.n + kAdofTile - 1) / kAdofTile;
   if (compact) adof_step_kernel<true><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);

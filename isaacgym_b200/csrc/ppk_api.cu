@@ -146,14 +146,8 @@ int launch_family(const KArgs& k, cudaStream_t s) {
   using L = FamilyLayout<H, J, D, A, TILE, OW>;
   auto kern = family_step_kernel<V, H, J, D, A, TILE, OW>;
   constexpr size_t smem = (size_t)L::kFloats * sizeof(float);
-  static bool configured = false;        // idempotent attribute; a benign race sets it twice
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      cudaGetLastError();
-      return PPK_ERR_LAUNCH;
-    }
-    configured = true;
-  }
+  static SmemOptIn opt;
+  if (!opt.ensure(kern, smem)) return PPK_ERR_LAUNCH;
   const long long tiles = (k.n + TILE - 1) / TILE;      // one CTA per tile
   kern<<<(unsigned)tiles, L::kThreads, smem, s>>>(k);
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
@@ -350,11 +344,8 @@ int rms_launch_moments(const PpkRunningMeanStd* rms, const RmsArgs& a, const flo
   const size_t smem = sizeof(double) * 2 * (vec ? 4 : 1) * R * wx;
   if (vec) {
     if (R < 8) return PPK_ERR_SHAPE;
-    static bool configured = false;
-    if (!configured) {
-      cudaFuncSetAttribute(rms_moments_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      configured = true;
-    }
+    static SmemOptIn opt;
+    if (!opt.ensure(rms_moments_kernel<4>, 96 * 1024)) return PPK_ERR_LAUNCH;
     rms_moments_kernel<4><<<(unsigned)blocks, dim3(wx, R), smem, s>>>(a, obs, rows, rms->moments, merge, (double)rows);
   } else {
     if (R < 2) return PPK_ERR_SHAPE;
@@ -476,17 +467,9 @@ int launch_first_layer(const FlArgs& k, cudaStream_t s) {
   CUtensorMap out_map;
   int rc = make_out_map(&out_map, k.out, k.rows, k.units);
   if (rc != PPK_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(first_layer_kernel<KP, KBLK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes) !=
-            cudaSuccess ||
-        cudaFuncSetAttribute(first_layer_kernel<KP, KBLK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes) !=
-            cudaSuccess) {
-      cudaGetLastError();
-      return PPK_ERR_LAUNCH;
-    }
-    configured = true;
-  }
+  static SmemOptIn opt0, opt1;
+  if (!opt0.ensure(first_layer_kernel<KP, KBLK, 0>, L::kBytes) || !opt1.ensure(first_layer_kernel<KP, KBLK, 1>, L::kBytes))
+    return PPK_ERR_LAUNCH;
   const long long units = ((k.rows + kFlM - 1) / kFlM) * (k.units / kFlN);
   const unsigned grid = (unsigned)(units < 148 ? units : 148);      // persistent: one CTA per SM
   if (k.activation == PPK_ACT_ELU) first_layer_kernel<KP, KBLK, 1><<<grid, kFlThreads, L::kBytes, s>>>(k, out_map);

@@ -11,6 +11,24 @@
 
 namespace ppk {
 
+// The opt-in dynamic shared-memory size is an attribute of (kernel, device): one of these per launcher
+// remembers the devices that already have it.  (A benign race sets the attribute twice.)
+struct SmemOptIn {
+  unsigned long long done = 0;
+  template <class Kernel>
+  bool ensure(Kernel kern, size_t bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (dev >= 0 && dev < 64 && ((done >> dev) & 1ull)) return true;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    if (dev >= 0 && dev < 64) done |= 1ull << dev;
+    return true;
+  }
+};
+
 constexpr int kRow = 13;  // floats per rigid-body / root-state row: pos3 quat4 linvel3 angvel3
 
 // Kernel arguments: the two C structs flattened, by value in param space.
