@@ -165,3 +165,23 @@ def test_first_layer_full_size_properties():
     ref.running_mean, ref.running_var = rms.running_mean.cpu(), rms.running_var.cpu()
     want = P.first_layer(ref.normalize(x[idx.to(DEV)].cpu()), w.cpu(), b.cpu(), "elu")
     assert_fp16_close(full[idx.to(DEV)], want, "full-size sample", ulps=2)
+
+
+@pytest.mark.parametrize("width,units", [(80, 2048), (313, 512)])
+def test_first_layer_against_torch_cuda_autocast(width, units):
+    """The thing the reference's learner actually runs: torch.autocast("cuda", float16) over
+    elu(linear(normalised obs)) -- cuBLAS fp16 GEMM (fp32 accumulate) + torch's elementwise kernels, on this GPU.
+    Same tolerance as against the CPU restatement (summation order inside the dot product)."""
+    rows = 8192
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(rows, width, device=DEV, generator=g) * 1.5 + 0.2
+    lin = torch.nn.Linear(width, units).to(DEV)
+    rms = RunningMeanStd(width, device=DEV)
+    rms.update(x)
+    rms.eval()
+    got = FirstLayer(lin.weight, lin.bias, "elu", rms)(x)
+    xn = rms.normalize(x)                                   # bit-exact fp32 normalisation (tested above)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        want = torch.nn.functional.elu(lin(xn))
+    assert want.dtype == torch.float16
+    assert_fp16_close(got, want.cpu(), f"torch cuda autocast width={width}", ulps=2)
