@@ -390,3 +390,27 @@ def test_full_size_yaw_invariance_of_observations(variant, n):
     # budget: the turn itself (fp32 sin / cos and two roundings per coordinate) plus atan2f / sinf / cosf of the
     # heading, a few 1e-6 rad on vectors up to ~10x the row scale
     assert float(err.max()) < 5e-5, f"max scaled deviation {float(err.max())}"
+
+
+@pytest.mark.parametrize("variant", [v for v in VARIANTS if v != "base"])
+@pytest.mark.parametrize("seed", [1, 2])
+def test_randomised_coefficients(variant, seed):
+    """The reward coefficients and the episode length are run-time parameters of PpkTask (YAML values in the
+    reference): random ones must flow through exactly as they do through the reference functions."""
+    import random
+    rnd = random.Random(100 * seed + CONFIGS[variant].variant_id)
+    base = CONFIGS[variant]
+    cfg = base.with_(
+        max_episode_length=rnd.randint(20, 300), alpha=rnd.uniform(1.0, 4000.0), power_coefficient=rnd.uniform(1e-4, 1e-2),
+        penalty=-rnd.uniform(10.0, 900.0), hit_table_reward=rnd.uniform(100.0, 5000.0),
+        not_hit_table_penalty=-rnd.uniform(100.0, 3000.0), cross_net_reward=rnd.uniform(10.0, 2000.0),
+        die_penalty=-rnd.uniform(100.0, 5000.0), hit_paddle_reward=rnd.uniform(10.0, 500.0),
+        miss_paddle_penalty_coefficient=-rnd.uniform(10.0, 300.0))
+    n = 3000
+    st = make_state(cfg, n, seed=500 + seed)
+    want, _ = oracle_full_step(cfg, st)
+    g = gpu_state(st)
+    run(cfg, g, N.PHASE_ALL)
+    ctx = f"{variant} random coefficients #{seed}"
+    assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, ctx)
+    assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], ctx)
