@@ -414,3 +414,23 @@ def test_randomised_coefficients(variant, seed):
     ctx = f"{variant} random coefficients #{seed}"
     assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, ctx)
     assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], ctx)
+
+
+@pytest.mark.parametrize("variant", ["tilt", "nes", "a4"])
+def test_scattered_body_ids_take_the_generic_staging_path(variant):
+    """`bodyStatesId` is a YAML list: ids that are not one run of consecutive rows (and a paddle that is not the
+    last id) make the library fall back from the bulk-copy windows to plain loads -- same results."""
+    base = CONFIGS[variant]
+    ids = (3, 7, 12, 13, 20, 26, 27, 33, 38, 39)                 # scattered, paddle row 39 last as in the reference
+    kw = dict(body_ids=ids)
+    if variant == "a4":
+        kw["body_ids_2"] = tuple(i + 40 for i in (1, 5, 9, 14, 15, 22, 30, 31, 36, 39))
+    cfg = base.with_(**kw)
+    n = 2000
+    st = make_state(cfg, n, seed=321)
+    want, _ = oracle_full_step(cfg, st)
+    g = gpu_state(st)
+    run(cfg, g, N.PHASE_ALL)
+    ctx = f"{variant} scattered ids"
+    assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, ctx)
+    assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], ctx)
