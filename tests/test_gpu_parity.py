@@ -434,3 +434,25 @@ def test_scattered_body_ids_take_the_generic_staging_path(variant):
     ctx = f"{variant} scattered ids"
     assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, ctx)
     assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], ctx)
+
+
+@pytest.mark.parametrize("variant", ["tilt", "adof", "a4"])
+def test_tensors_that_are_only_4_byte_aligned(variant):
+    """State tensors handed over as views that start 4 bytes into an allocation (legal for fp32 data) cannot be
+    bulk-copied in 16-byte pieces: the library takes its plain-load path -- same results."""
+    cfg = CONFIGS[variant]
+    n = 1500
+    st = make_state(cfg, n, seed=77)
+    want, _ = oracle_full_step(cfg, st)
+    g = gpu_state(st)
+    for key in ("rigid_body_states", "root_states", "dof_states", "dof_forces", "initial_body_states"):
+        if key in g:
+            t = g[key]
+            flat = torch.empty(t.numel() + 1, dtype=t.dtype, device=DEV)
+            flat[1:].copy_(t.reshape(-1))
+            g[key] = flat[1:].view(t.shape)
+            assert g[key].data_ptr() % 16 != 0 and g[key].is_contiguous()
+    run(cfg, g, N.PHASE_ALL)
+    ctx = f"{variant} misaligned"
+    assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, ctx)
+    assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], ctx)
