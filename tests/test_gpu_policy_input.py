@@ -185,3 +185,25 @@ def test_first_layer_against_torch_cuda_autocast(width, units):
         want = torch.nn.functional.elu(lin(xn))
     assert want.dtype == torch.float16
     assert_fp16_close(got, want.cpu(), f"torch cuda autocast width={width}", ulps=2)
+
+
+def test_first_layer_with_a_4_byte_aligned_observation_view():
+    """obs handed over as a view that starts 4 bytes into an allocation: the row-tile preparation takes scalar
+    loads instead of 16-byte ones, the moments / normalise kernels their one-column layout -- same results."""
+    rows, width, units = 3000, 80, 512
+    g = torch.Generator(device=DEV).manual_seed(9)
+    flat = torch.randn(rows * width + 1, device=DEV, generator=g)
+    x = flat[1:].view(rows, width)
+    assert x.data_ptr() % 16 != 0 and x.is_contiguous()
+    xa = x.clone()                                            # the same values, 16-byte aligned
+    w = torch.randn(units, width, device=DEV, generator=g) / width ** 0.5
+    b = torch.randn(units, device=DEV, generator=g) * 0.1
+    r1, r2 = RunningMeanStd(width, device=DEV), RunningMeanStd(width, device=DEV)
+    r1.update(x)
+    r2.update(xa)
+    torch.testing.assert_close(r1.running_mean, r2.running_mean, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(r1.running_var, r2.running_var, rtol=1e-12, atol=1e-12)
+    r1.eval(); r2.eval()
+    r2.running_mean.copy_(r1.running_mean); r2.running_var.copy_(r1.running_var)
+    assert torch.equal(r1.normalize(x), r2.normalize(xa))
+    assert torch.equal(FirstLayer(w, b, "elu", r1)(x), FirstLayer(w, b, "elu", r2)(xa))
