@@ -151,8 +151,9 @@ family_step_kernel(const __grid_constant__ KArgs k) {
 #pragma unroll
       for (int c = 0; c < 10; ++c) r0[c] = ld_stream(g0 + c);
     }
-    if (bulk) mbar_wait(bar, 0);
-    PPK_STAMP(2);
+    // On the bulk path the frames need only the plain-loaded root rows: compute them while the row windows are
+    // still in flight and wait for those afterwards.
+    if (!bulk) PPK_STAMP(2);
     // heading frames of this warp's units u = OW*lane + (warp-1)
     if (frame_lane) {
       const int e = fu / H, h = fu - e * H;
@@ -172,6 +173,10 @@ family_step_kernel(const __grid_constant__ KArgs k) {
       hd[3] = __int_as_float(off1);
     }
     hdr_arrive(kFamilyThreads);       // warp 0 needs the frames for the ball
+    if (bulk) {
+      mbar_wait(bar, 0);
+      PPK_STAMP(2);
+    }
     __syncwarp();
     // lane = output float o of a 3J-float segment: body j = o/3, component c = o%3.
     //   out_c = v_c*a0 + ((s1*v_o)*m)*2 with (s1, o, m) = (-sz, y, cw) / (sz, x, cw) / (sz, z, sz)
