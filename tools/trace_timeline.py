@@ -8,7 +8,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 cfg = CONFIGS["tilt"]
 lib = N.load()
 tasks = [make_task("tilt", make_state(cfg, n, seed=s, device="cuda", adversarial=False), device="cuda") for s in range(4)]
-blocks = (n + 31)//32
+blocks = (n + 15)//16        # TILE = 16 (A3 / TILT / NES / ALIGN)
 buf = torch.zeros(blocks*8*4, dtype=torch.int64, device="cuda")
 lib.ppk_debug_set_trace.argtypes=[C.c_void_p]
 for t in tasks: t._step(N.PHASE_ALL & ~N.PHASE_STATS)
@@ -21,16 +21,16 @@ buf.zero_(); torch.cuda.synchronize()
 ev0.record(); tasks[1]._step(N.PHASE_ALL & ~N.PHASE_STATS); ev1.record(); torch.cuda.synchronize()
 print("event time us", ev0.elapsed_time(ev1)*1e3)
 tr = buf.cpu().numpy().reshape(blocks, 8, 4).astype(np.int64)
-t0 = tr[:, :5, 0]; base = t0[t0>0].min()
+t0 = tr[:, :3, 0]; base = t0[t0>0].min()
 def rel(x): return (x - base)/1e3
-start = rel(tr[:,0,0]); issued = rel(tr[:,:5,1]); arrived = rel(tr[:,:5,2]); done = rel(tr[:,:5,3])
+start = rel(tr[:,0,0]); issued = rel(tr[:,:3,1]); arrived = rel(tr[:,:3,2]); done = rel(tr[:,:3,3])
 print("resolution check: unique deltas (ns)", np.unique(np.diff(np.sort(tr[:,0,0])))[:8])
 q = lambda a: np.percentile(a, [0, 10, 50, 90, 100]).round(2)
 print("CTA start (us since first)      p0/10/50/90/100:", q(start))
 print("issue done - start, warp0               :", q(issued[:,0]-start))
 print("data arrived - issue done, warp0        :", q(arrived[:,0]-issued[:,0]))
 print("warp0 compute (end - arrived)           :", q(done[:,0]-arrived[:,0]))
-print("obs warps compute (end - arrived)       :", q((done[:,1:5]-arrived[:,1:5]).ravel()))
+print("obs warps compute (end - arrived)       :", q((done[:,1:3]-arrived[:,1:3]).ravel()))
 print("CTA lifetime (max end - start)          :", q(done.max(axis=1)-start))
 print("kernel span (last end - first start) us :", done.max() - start.min())
 # how many CTAs are alive over time
@@ -44,10 +44,10 @@ print("count", late.sum())
 print("issue done - start, warp0   :", q((issued[:,0]-start)[late]))
 print("arrived - issue done, warp0 :", q((arrived[:,0]-issued[:,0])[late]))
 print("warp0 compute               :", q((done[:,0]-arrived[:,0])[late]))
-print("obs compute                 :", q((done[:,1:5]-arrived[:,1:5])[late].ravel()))
+print("obs compute                 :", q((done[:,1:3]-arrived[:,1:3])[late].ravel()))
 print("lifetime                    :", q((done.max(axis=1)-start)[late]))
 vl = start > 11.0
 print("---- very late CTAs (start > 11 us): count", vl.sum())
-print("issue:", q((issued[:,0]-start)[vl]), "wait:", q((arrived[:,0]-issued[:,0])[vl]), "w0 compute:", q((done[:,0]-arrived[:,0])[vl]), "obs compute:", q((done[:,1:5]-arrived[:,1:5])[vl].ravel()), "life:", q((done.max(axis=1)-start)[vl]))
-print("per-warp issue-done minus start (all CTAs), warps 0..4 median:", [float(np.median(issued[:,w]-start)) for w in range(5)])
-print("obs warp end - warp0 end median:", float(np.median(done[:,1:5].max(axis=1) - done[:,0])))
+if vl.sum() > 0: print("issue:", q((issued[:,0]-start)[vl]), "wait:", q((arrived[:,0]-issued[:,0])[vl]), "w0 compute:", q((done[:,0]-arrived[:,0])[vl]), "obs compute:", q((done[:,1:3]-arrived[:,1:3])[vl].ravel()), "life:", q((done.max(axis=1)-start)[vl]))
+print("per-warp issue-done minus start (all CTAs), warps 0..4 median:", [float(np.median(issued[:,w]-start)) for w in range(3)])
+print("obs warp end - warp0 end median:", float(np.median(done[:,1:3].max(axis=1) - done[:,0])))
