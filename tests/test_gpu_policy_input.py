@@ -19,7 +19,7 @@ def batch(rows, width, seed, scale=2.0, shift=0.7):
     return torch.randn(rows, width, generator=g) * scale + shift
 
 
-@pytest.mark.parametrize("width", [80, 94, 313, 24])
+@pytest.mark.parametrize("width", [80, 94, 313, 24, 1, 512])      # 1: rl_games' value normalisation (normalize_value)
 def test_running_mean_std_matches_restatement(width):
     ours = RunningMeanStd(width, device=DEV)
     ref = P.RunningMeanStd(width)
