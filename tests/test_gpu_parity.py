@@ -456,3 +456,23 @@ def test_tensors_that_are_only_4_byte_aligned(variant):
     ctx = f"{variant} misaligned"
     assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, ctx)
     assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], ctx)
+
+
+def test_host_session_full_size_tilt():
+    """The e2e path of bench.py at its own size: 65 536 envs, pinned host tensors, 4 pipeline chunks, graph replay
+    from the third call on -- bit-identical to the device path for four consecutive steps."""
+    from isaacgym_b200.host_session import HostSession
+    cfg = CONFIGS["tilt"]
+    n = 65536
+    st = make_state(cfg, n, seed=4242, adversarial=False)
+    dev = gpu_state(st)
+    dev["pre_ball_states"] = dev["pre_ball_states"][:, [7, 9]].contiguous()
+    sess = HostSession(cfg, st, num_chunks=4, pin=True)
+    try:
+        for step in range(4):
+            sess.post_physics_step(N.PHASE_ALL & ~N.PHASE_STATS)
+            run(cfg, dev, N.PHASE_ALL & ~N.PHASE_STATS)
+            for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names:
+                assert torch.equal(sess.state[name], dev[name].cpu()), f"step {step}: {name}"
+    finally:
+        sess.close()
