@@ -115,3 +115,13 @@ def test_learner_side_argument_validation(lib):
     assert lib.ppk_policy_first_layer(None, 0x1000, 16, 80, 0x1000, 2048, 7, 0x1000, None) == -4   # activation
     assert lib.ppk_policy_first_layer(None, None, 16, 80, 0x1000, 2048, 1, 0x1000, None) == -1
     assert lib.ppk_policy_first_layer(None, 0x1000, 0, 80, 0x1000, 2048, 1, 0x1000, None) == 0     # empty batch
+
+
+def test_learner_side_host_mirror_is_cuda_only():
+    """No CPU or torch fallback behind the host mirrors: they refuse to exist on the CPU."""
+    import torch
+    from isaacgym_b200.policy_input import FirstLayer, RunningMeanStd
+    with pytest.raises(RuntimeError):
+        RunningMeanStd(80, device="cpu")
+    with pytest.raises(RuntimeError):
+        FirstLayer(torch.zeros(256, 80), torch.zeros(256))
