@@ -93,33 +93,6 @@ family_step_kernel(const __grid_constant__ KArgs k) {
   const int env_stride = k.B * kRow;
   const float* g_rb = k.rb + (size_t)env0 * env_stride;
 
-  // ---- the lines of the plain loads first ---------------------------------------------------------------
-  // The per-env scalars (warp 0) and the root-body rows (obs warps) are plain loads issued after the bulk copies:
-  // they queue behind ~15 KB of row windows per CTA and come back ~1.4 us after them (timeline), which is warp
-  // 0's critical path.  Requesting their lines into L2 before anything else costs no registers.
-  if (bulk) {
-    if (warp == 0) {
-      if (lane < TILE) {
-        const char* r = reinterpret_cast<const char*>(k.root + (size_t)(env0 + lane) * L::kRootEnv);
-        prefetch_l2(r + 4 * k.ball * kRow);
-        prefetch_l2(r + 4 * k.ball * kRow + 36);
-        prefetch_l2(r + 4 * k.hum[0] * kRow);
-      } else if (lane == TILE) {
-        prefetch_l2(k.progress + env0);
-      } else if (lane == TILE + 1) {
-        if (k.pre != nullptr) prefetch_l2(k.pre + (size_t)env0 * k.pre_stride);
-      } else if (lane - (TILE + 2) < 6 && k.flags[lane - (TILE + 2)] != nullptr && (phases & PPK_PHASE_REWARD)) {
-        prefetch_l2(k.flags[lane - (TILE + 2)] + env0);
-      }
-    } else if (lane < L::kUnits / kObsWarps) {
-      const int u = kObsWarps * lane + (warp - 1);
-      const int e = u / H, h = u - e * H;
-      const float* g0 = g_rb + (size_t)e * env_stride + k.ids[h][0] * kRow;
-      prefetch_l2(g0);
-      prefetch_l2(g0 + 9);
-    }
-  }
-
   // ---- stage ---------------------------------------------------------------------------------------
   PPK_STAMP(0);
   if (bulk) {
