@@ -50,7 +50,7 @@ ALGO_BYTES = {"base": 212 + 8, "a3": 708 + 8, "tilt": 718 + 8, "nes": 716 + 8, "
 PRE_STEP_BYTES = {"align": 72}
 OTHER_STEPS = 2048          # timed steps of each context workload (other_workloads)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the ncu --set full captures under profiles/
-NCU_TRAFFIC = {("tilt", 65536): 65.5e6 + 3.2e6, ("adof", 32768): 147.26e6 + 21.6e6, ("a4", 65536): 116.09e6 + 16.6e6}
+NCU_TRAFFIC = {("tilt", 65536): 68.15e6 + 3.0e6, ("adof", 32768): 113.55e6 + 15.8e6, ("a4", 65536): 116.09e6 + 16.6e6}
 
 
 def measured_hbm_peak():
