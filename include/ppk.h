@@ -33,7 +33,7 @@ extern "C" {
 #define PPK_API
 #endif
 
-#define PPK_ABI_VERSION 1
+#define PPK_ABI_VERSION 2
 #define PPK_MAX_BODY_IDS 32   /* J: rows gathered by the observation functions        */
 #define PPK_MAX_FLAGS 12      /* bool flag / counter tensors of one variant            */
 #define PPK_STATS_SLOTS 64    /* stats[PPK_STATS_SLOTS][PPK_NUM_STATS] partial sums     */
@@ -192,6 +192,10 @@ typedef struct PpkBuffers {
    * When non-NULL the step reads this instead of initial_body_states (552 B per env instead of 28
    * rigid-body rows); the caller keeps it in sync if it ever rewrites the reference pose. */
   const float* initial_balance_states;
+  /* VecTask.step envelope: > 0 clamps every observation to +-clip_observations where the step kernels
+   * produce it (upstream VecTask.step: obs = clamp(obs_buf, -clip_obs, clip_obs); the upstream default
+   * is inf = no clamp, and no YAML of the reference sets clipObservations).  <= 0: off. */
+  float clip_observations;
 } PpkBuffers;
 
 PPK_API int ppk_abi_version(void);

@@ -11,7 +11,7 @@ PPK_MAX_BODY_IDS = 32
 PPK_MAX_FLAGS = 12
 PPK_STATS_SLOTS = 64
 PPK_NUM_STATS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 PHASE_PROGRESS, PHASE_REWARD, PHASE_RESET, PHASE_OBS, PHASE_STATS = 1, 2, 4, 8, 16
 PHASE_ALL = 31
@@ -53,6 +53,7 @@ class PpkBuffers(C.Structure):
         ("actor_indices", C.c_void_p), ("dof_indices", C.c_void_p), ("reset_count", C.c_void_p),
         ("reset_actor_indices", C.c_void_p), ("reset_dof_indices", C.c_void_p),
         ("last_hitter", C.c_void_p), ("initial_balance_states", C.c_void_p),
+        ("clip_observations", C.c_float),
     ]
 
 
@@ -235,6 +236,8 @@ def make_buffers(cfg: TaskConfig, st: dict, host: bool = False) -> PpkBuffers:
     b.last_hitter = _ptr(st.get("last_hitter"), i64, "last_hitter", host)
     # optional VecTask.step envelope outputs
     b.clip_actions = float(st.get("clip_actions", 0.0) or 0.0)
+    clip_obs = float(st.get("clip_observations", 0.0) or 0.0)
+    b.clip_observations = clip_obs if (clip_obs > 0.0 and clip_obs != float("inf")) else 0.0
     b.timeout_buf = _ptr(st.get("timeout_buf"), i64, "timeout_buf", host)
     if st.get("reset_count") is not None:
         ai, di = st["actor_indices"], st["dof_indices"]

@@ -37,14 +37,15 @@ def _source_hash():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None):
+    """`out`: build a variant (PPK_NVCC_EXTRA) somewhere else, e.g. scratch/libs/x.so for A/B runs with PPK_LIB."""
     os.makedirs(LIB_DIR, exist_ok=True)
     want = _source_hash()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP) and open(STAMP).read().strip() == want:
+    if out is None and not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP) and open(STAMP).read().strip() == want:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB_PATH] + srcs
     if verbose:
         print(" ".join(cmd), flush=True)
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -53,11 +54,14 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libppk.so")
     if verbose:
         print(res.stdout + res.stderr)
+    if out is not None:
+        return out
     with open(STAMP, "w") as f:
         f.write(want)
     return LIB_PATH
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=out)
     print(p)

@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(kAdofThreads, COMPACT ? PPK_ADOF_MINB : 6)
 adof_step_kernel(const __grid_constant__ KArgs k) {
   using L = AdofLayout<COMPACT>;
   extern __shared__ __align__(128) float smem[];
-  const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float clip = k.clip_obs;
   const long long env0 = (long long)blockIdx.x * kAdofTile;
   const int nvalid = (int)min((long long)kAdofTile, k.n - env0);
   constexpr int D = kAdofD, J = kAdofJ, NB = kAdofNB, T = kAdofTile;
@@ -222,8 +222,8 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
           const float* row = rb_e + k.ids[0][j] * kRow;
           const float pc = row[c] - r0[c], po = row[oth] - r0[oth];
           float* orow = g_obs + (size_t)e * kAdofObs;
-          st_stream(orow + lane, pc * a0 + ((s1 * po) * m) * 2.0f);
-          st_stream(orow + 3 * J + lane, row[7 + c] * a0 + ((s1 * row[7 + oth]) * m) * 2.0f);
+          st_stream(orow + lane, clip_opt(pc * a0 + ((s1 * po) * m) * 2.0f, clip));
+          st_stream(orow + 3 * J + lane, clip_opt(row[7 + c] * a0 + ((s1 * row[7 + oth]) * m) * 2.0f, clip));
         }
         // imitation observation segments [121,190) = 10*R(dP), [190,259) = R(dV)
         float lp[3], lv[3];
@@ -242,8 +242,8 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
         __syncwarp();
 #pragma unroll
         for (int o = lane; o < 3 * NB; o += 32) {
-          st_stream(orow + o, tr[o]);
-          st_stream(orow + 3 * NB + o, tr[3 * NB + o]);
+          st_stream(orow + o, clip_opt(tr[o], clip));
+          st_stream(orow + 3 * NB + o, clip_opt(tr[3 * NB + o], clip));
         }
       }
     }
@@ -431,7 +431,7 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
     oo = (l < kSegA) ? (6 * J + l) : (6 * J + kSegA + 6 * NB + (l - kSegA));
 #pragma unroll
     for (int e = 0; e < T; ++e)
-      if (e < nvalid) st_stream(g_obs + (size_t)e * kAdofObs + oo, src[e * stride] * scale);
+      if (e < nvalid) st_stream(g_obs + (size_t)e * kAdofObs + oo, clip_opt(src[e * stride] * scale, clip));
   }
 }
 

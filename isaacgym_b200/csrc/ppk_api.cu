@@ -1,6 +1,7 @@
 // C ABI (include/ppk.h) over the sm_100a kernels.  No torch types, no allocation, no host sync.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/ppk.h"
@@ -13,6 +14,25 @@
 using namespace ppk;
 
 namespace {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
 
 int fill_args(const PpkTask* t, const PpkBuffers* b, uint32_t phases, KArgs* k) {
   if (t == nullptr || b == nullptr) return PPK_ERR_NULL;
@@ -77,20 +97,37 @@ int fill_args(const PpkTask* t, const PpkBuffers* b, uint32_t phases, KArgs* k) 
   k->die_penalty = t->die_penalty; k->hit_paddle = t->hit_paddle_reward; k->miss_coef = t->miss_paddle_penalty_coefficient;
   k->term_dist = t->is_train ? 0.32f : 1e6f;           // ADOF:1404-1410, is_g1 branch
   k->phases = (int)phases; k->write_flags = t->write_flags; k->reset_dof = t->reset_dof;
-  // Bulk async staging (cp.async.bulk) moves 16-byte aligned windows around each env's rows: legal
-  // when the tensors start 16-byte aligned, ids[1..J) are consecutive rows (one run per env) and a
-  // further row follows ids[0] and ids[J-1] inside the env block (the windows over-read <= 12 bytes).
-  bool bulk = t->num_body_ids >= 2 && b->rigid_body_states && b->root_states && b->dof_states && b->dof_forces;
+  k->clip_obs = b->clip_observations;
+  // Tensor-map staging (family kernel): the rigid-body tensor is read as [N/2 env pairs, 2*B*13 floats], legal when
+  // the tensors start 16-byte aligned, an env pair is a multiple of 16 bytes (B even), ids[1..J) are consecutive rows
+  // (one run per env).  The boxes over-read <= 12 bytes on either side of a run; what falls outside a pair's row of
+  // the tensor is zero-filled by the engine, never fetched.  Bit 0: loads, bit 1: the obs tile may be written back
+  // with one bulk copy.
+  bool bulk = t->num_body_ids >= 2 && b->rigid_body_states && b->root_states && b->dof_states && b->dof_forces &&
+              (t->num_bodies % 2 == 0) && b->num_envs >= 2;
+  const int nh = (t->variant == PPK_A4 || t->variant == PPK_ALIGN2) ? 2 : 1;
   if (bulk) {
     const void* al[] = {b->rigid_body_states, b->root_states, b->dof_states, b->dof_forces};
     for (const void* p : al) bulk = bulk && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
-    const int nh = (t->variant == PPK_A4 || t->variant == PPK_ALIGN2) ? 2 : 1;
     for (int h = 0; h < nh && bulk; ++h) {
       for (int j = 2; j < t->num_body_ids; ++j) bulk = bulk && (t->body_ids[h][j] == t->body_ids[h][1] + j - 1);
-      bulk = bulk && (t->body_ids[h][0] + 1 < t->num_bodies) && (t->body_ids[h][t->num_body_ids - 1] + 1 < t->num_bodies);
     }
   }
   k->bulk_ok = bulk ? 1 : 0;
+  if (bulk && b->obs_buf && (reinterpret_cast<uintptr_t>(b->obs_buf) & 15u) == 0) k->bulk_ok |= 2;
+  k->row0_box = kRow0Max;
+  if (bulk) {
+    int max_off = 0;
+    for (int h = 0; h < nh; ++h)
+      for (int q = 0; q < 2; ++q) {
+        const int s0 = q * t->num_bodies * kRow + t->body_ids[h][1] * kRow;
+        const int r0 = q * t->num_bodies * kRow + t->body_ids[h][0] * kRow;
+        k->span_c[h][q] = s0 & ~3; k->span_off[h][q] = s0 & 3;
+        k->row0_c[h][q] = r0 & ~3; k->row0_off[h][q] = r0 & 3;
+        if ((r0 & 3) > max_off) max_off = r0 & 3;
+      }
+    k->row0_box = (max_off + 10 <= 12) ? 12 : 16;
+  }
   return PPK_OK;
 }
 
@@ -141,15 +178,65 @@ int check_step_pointers(const PpkTask* t, const PpkBuffers* b, uint32_t phases) 
   return PPK_OK;
 }
 
-template <int V, int H, int J, int D, int A, int TILE, int OW>
-int launch_family(const KArgs& k, cudaStream_t s) {
-  using L = FamilyLayout<H, J, D, A, TILE, OW>;
-  auto kern = family_step_kernel<V, H, J, D, A, TILE, OW>;
+// soft-start delay per first-wave slot, in SM cycles (profiles/r2_staging_probe.md); PPK_STAGGER overrides it
+int stagger_cycles() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PPK_STAGGER");
+    v = e ? atoi(e) : 400;
+    if (v < 0) v = 0;
+  }
+  return v;
+}
+
+// the rigid-body tensor as [N/2 env pairs, 2*B*13 floats]; box = `box_floats` x `pairs` pairs
+int make_rb_map(CUtensorMap* m, const float* rb, long long n, int num_bodies, int box_floats, int pairs) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return PPK_ERR_CUDA;
+  const cuuint64_t dims[2] = {(cuuint64_t)2 * num_bodies * kRow, (cuuint64_t)(n / 2)};
+  const cuuint64_t strides[1] = {(cuuint64_t)2 * num_bodies * kRow * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_floats, (cuuint32_t)pairs};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(rb), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? PPK_OK
+             : PPK_ERR_CUDA;
+}
+
+template <int V, int H, int J, int D, int A, int TILE>
+int launch_family(const KArgs& k0, cudaStream_t s) {
+  using L = FamilyLayout<H, J, D, A, TILE>;
+  auto kern = family_step_kernel<V, H, J, D, A, TILE>;
   constexpr size_t smem = (size_t)L::kFloats * sizeof(float);
   static SmemOptIn opt;
   if (!opt.ensure(kern, smem)) return PPK_ERR_LAUNCH;
+  KArgs k = k0;
+  CUtensorMap m_span, m_row0;
+  memset(&m_span, 0, sizeof(m_span));
+  memset(&m_row0, 0, sizeof(m_row0));
   const long long tiles = (k.n + TILE - 1) / TILE;      // one CTA per tile
-  kern<<<(unsigned)tiles, L::kThreads, smem, s>>>(k);
+  if (k.bulk_ok & 1) {
+    if (make_rb_map(&m_span, k.rb, k.n, k.B, L::kSpanF, L::kPairs) != PPK_OK ||
+        make_rb_map(&m_row0, k.rb, k.n, k.B, k.row0_box, L::kPairs) != PPK_OK)
+      k.bulk_ok = 0;                                     // no driver entry point: the LDG path still works
+  }
+  // soft start: only when the grid does not fit the GPU at once
+  static int occ = 0, sms = 0;
+  if (occ == 0) {
+    int dev = 0, o = 0, n_sm = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kFamilyThreads, smem) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && o > 0 && n_sm > 0) {
+      sms = n_sm;
+      occ = o;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  k.num_sms = sms > 0 ? sms : 1;
+  k.first_wave = occ * sms;
+  k.stagger = (occ > 0 && tiles > (long long)occ * sms) ? stagger_cycles() : 0;
+  kern<<<(unsigned)tiles, kFamilyThreads, smem, s>>>(k, m_span, m_row0);
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 
@@ -195,16 +282,16 @@ int ppk_post_physics_step(const PpkTask* t, const PpkBuffers* b, uint32_t phases
     case PPK_NES:
     case PPK_ALIGN:
       if (t->num_actors != 3 || t->num_dofs != 7 || t->num_body_ids != 10) return PPK_ERR_SHAPE;
-      if (t->variant == PPK_A3) return launch_family<PPK_A3, 1, 10, 7, 3, 16, 2>(k, s);
-      if (t->variant == PPK_TILT) return launch_family<PPK_TILT, 1, 10, 7, 3, 16, 2>(k, s);
-      if (t->variant == PPK_NES) return launch_family<PPK_NES, 1, 10, 7, 3, 16, 2>(k, s);
-      return launch_family<PPK_ALIGN, 1, 10, 7, 3, 16, 2>(k, s);
+      if (t->variant == PPK_A3) return launch_family<PPK_A3, 1, 10, 7, 3, 32>(k, s);
+      if (t->variant == PPK_TILT) return launch_family<PPK_TILT, 1, 10, 7, 3, 32>(k, s);
+      if (t->variant == PPK_NES) return launch_family<PPK_NES, 1, 10, 7, 3, 32>(k, s);
+      return launch_family<PPK_ALIGN, 1, 10, 7, 3, 32>(k, s);
     case PPK_A4:
       if (t->num_actors != 4 || t->num_dofs != 14 || t->num_body_ids != 10) return PPK_ERR_SHAPE;
-      return launch_family<PPK_A4, 2, 10, 14, 4, 8, 1>(k, s);
+      return launch_family<PPK_A4, 2, 10, 14, 4, 16>(k, s);
     case PPK_ALIGN2:
       if (t->num_actors != 4 || t->num_dofs != 14 || t->num_body_ids != 10) return PPK_ERR_SHAPE;
-      return launch_family<PPK_ALIGN2, 2, 10, 14, 4, 8, 1>(k, s);
+      return launch_family<PPK_ALIGN2, 2, 10, 14, 4, 16>(k, s);
     case PPK_ADOF:
       if (t->num_actors != 3 || t->num_dofs != 27 || t->num_body_ids != 10 || t->num_balance_ids != 23) return PPK_ERR_SHAPE;
       return launch_adof(k, s);
@@ -428,25 +515,6 @@ int ppk_linear_pack(const float* weight, const float* bias, int32_t units, int32
 
 extern "C++" {
 namespace {
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess) {
-      cudaGetLastError();
-      return nullptr;
-    }
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 // out [rows, units] fp16 as a 2-D tensor; box = one epilogue warp's [32 rows x 64 units] tile, 128B swizzle
 int make_out_map(CUtensorMap* m, void* out, long long rows, int units) {
   EncodeTiledFn enc = encode_tiled_fn();

@@ -88,4 +88,26 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// 2-D tiled tensor copy global -> shared (SASS: UTMALDG): box of the tensor map at element coordinates (c0, c1);
+// dst 128-byte aligned; the inner coordinate c0 must start on a 16-byte boundary (measured: otherwise the
+// instruction faults, profiles/r2_staging_probe.md).
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tensor_map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// shared -> global bulk copy (SASS: UBLKCP.G.S); dst, src 16-byte aligned, bytes a multiple of 16.  The writes to the
+// source made through the generic proxy must be fenced (fence_proxy_async) and ordered (barrier) before the issue.
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the issuing thread may not exit (shared memory is released) before the source has been read
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 }  // namespace ppk

@@ -79,6 +79,15 @@ struct KArgs {
   int* reset_count;
   int* reset_actor_out;
   int* reset_dof_out;
+  float clip_obs;            // > 0: observations are clamped to +-clip_obs where they are produced (VecTask.step)
+  // tensor-map staging of the rigid-body rows (family kernel): inner coordinates (floats, 16-byte aligned) of the
+  // boxes [humanoid][env parity] and where the wanted rows start inside them
+  int span_c[2][2], span_off[2][2];
+  int row0_c[2][2], row0_off[2][2];
+  int row0_box;              // floats per staged ids[0] row (12 or 16)
+  // soft start of the first wave (profiles/r2_staging_probe.md): CTA b < first_wave delays its loads by
+  // (b / num_sms) * stagger cycles
+  int stagger, first_wave, num_sms;
 };
 
 // Append env `env`'s actor / dof indices to the compacted reset lists (TILT:876-877).  Called by a
@@ -127,6 +136,11 @@ __device__ __forceinline__ float warp_sum8(float v0, float v1, float v2, float v
   y += __shfl_xor_sync(full, y, 1);
   return y;
 }
+
+// VecTask.step's observation clamp (torch.clamp(obs_buf, -c, c): NaN passes through), applied where an
+// observation is produced; c <= 0 means no clamp (the upstream default is inf)
+__device__ __forceinline__ float clip_to(float v, float c) { return (v < -c) ? -c : ((v > c) ? c : v); }
+__device__ __forceinline__ float clip_opt(float v, float c) { return (c > 0.0f) ? clip_to(v, c) : v; }
 
 // streaming loads/stores: every byte of state is touched once per step
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }

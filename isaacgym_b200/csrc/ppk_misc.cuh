@@ -78,7 +78,7 @@ base_step_kernel(const __grid_constant__ KArgs k) {
 #pragma unroll
     for (int i = 0; i < kBaseObs; ++i) {
       int f = i * 32 + lane, e = f / kBaseObs, c = f - e * kBaseObs;
-      if (e < nvalid) st_stream(g + f, obs_s[warp][e * (kBaseObs + 1) + c]);
+      if (e < nvalid) st_stream(g + f, clip_opt(obs_s[warp][e * (kBaseObs + 1) + c], k.clip_obs));
     }
   }
   if (phases & PPK_PHASE_REWARD) {

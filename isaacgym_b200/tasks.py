@@ -112,7 +112,8 @@ class PingpongTask(VecTask):
         d = dict(self.st)
         d.update(obs_buf=self.obs_buf, rew_buf=self.rew_buf, reset_buf=self.reset_buf, progress_buf=self.progress_buf,
                  pre_ball_states=self.pre_ball2_root_states, actions=self.actions, pd_targets=self.pd_tar,
-                 stats=self.stats.slots, scratch=self._scratch, clip_actions=self.clip_actions)
+                 stats=self.stats.slots, scratch=self._scratch, clip_actions=self.clip_actions,
+                 clip_observations=self.clip_obs)
         if self.envelope:
             d.update(timeout_buf=self.timeout_buf)
         if self.envelope and "actor_indices" in self.st and "dof_indices" in self.st:

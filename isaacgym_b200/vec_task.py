@@ -5,6 +5,9 @@ dtypes and the `step()` call order -- and nothing else (no viewer, no randomisat
 step(actions) (upstream VecTask.step):
     clamp actions to +-clipActions -> pre_physics_step(actions) -> simulate x control_freq_inv
     -> post_physics_step() -> clamp obs to +-clipObservations -> (obs, rew_buf, reset_buf, extras)
+Both clamps happen inside the CUDA kernels (`PpkBuffers.clip_actions`, `PpkBuffers.clip_observations`): no ATen
+kernel runs between `pre_physics_step` and the returned observations.  `clip_observations` defaults to upstream's
+`inf` (no clamp; none of the reference's YAMLs sets clipObservations).
 PhysX is replaced by a `physics` callable that refreshes the synthetic state tensors in place.
 """
 from typing import Callable, Dict, Optional
@@ -16,7 +19,7 @@ from .config import TaskConfig
 
 class VecTask:
     def __init__(self, cfg: TaskConfig, num_envs: int, device: str = "cuda:0", clip_actions: float = 1.0,
-                 clip_observations: float = 5.0, control_freq_inv: int = 1,
+                 clip_observations: float = float("inf"), control_freq_inv: int = 1,
                  physics: Optional[Callable[["VecTask"], None]] = None):
         self.cfg = cfg
         self.num_envs = num_envs
@@ -62,5 +65,5 @@ class VecTask:
         # the reset cleared it); otherwise it stays zero as in the reference, whose reset has already
         # cleared progress_buf by the time upstream VecTask.step evaluates it
         self.extras["time_outs"] = self.timeout_buf
-        obs = torch.clamp(self.obs_buf, -self.clip_obs, self.clip_obs)
-        return {"obs": obs}, self.rew_buf, self.reset_buf, self.extras
+        # obs_buf is already clamped to +-clip_observations where the step kernel produced it
+        return {"obs": self.obs_buf}, self.rew_buf, self.reset_buf, self.extras

@@ -1,53 +1,47 @@
-import ctypes as C, sys, torch, numpy as np
-sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
+"""Per-CTA timeline of one launch of the family step kernel (needs a -DPPK_TRACE build):
+    PPK_NVCC_EXTRA=-DPPK_TRACE python -m isaacgym_b200.build --out scratch/libs/libppk_trace.so
+    PPK_LIB=scratch/libs/libppk_trace.so python tools/trace_timeline.py [envs] [variant]
+Stamps per warp (globaltimer ns): 0 CTA start, 1 copies issued, 2 data arrived, 3 warp done."""
+import ctypes as C, os, sys, torch, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from isaacgym_b200 import _native as N
 from isaacgym_b200.config import CONFIGS
 from isaacgym_b200.synth import make_state
 from isaacgym_b200.tasks import make_task
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-cfg = CONFIGS["tilt"]
+variant = sys.argv[2] if len(sys.argv) > 2 else "tilt"
+cfg = CONFIGS[variant]
 lib = N.load()
-tasks = [make_task("tilt", make_state(cfg, n, seed=s, device="cuda", adversarial=False), device="cuda") for s in range(4)]
-blocks = (n + 15)//16        # TILE = 16 (A3 / TILT / NES / ALIGN)
-buf = torch.zeros(blocks*8*4, dtype=torch.int64, device="cuda")
-lib.ppk_debug_set_trace.argtypes=[C.c_void_p]
-for t in tasks: t._step(N.PHASE_ALL & ~N.PHASE_STATS)
+tasks = [make_task(variant, make_state(cfg, n, seed=s, device="cuda", adversarial=False), device="cuda") for s in range(4)]
+tile = 16 if variant in ("a4", "align2") else 32
+blocks = (n + tile - 1) // tile
+buf = torch.zeros(blocks * 8 * 4, dtype=torch.int64, device="cuda")
+lib.ppk_debug_set_trace.argtypes = [C.c_void_p]
+ph = N.PHASE_ALL & ~N.PHASE_STATS
+for t in tasks: t._step(ph)
 torch.cuda.synchronize()
 assert lib.ppk_debug_set_trace(buf.data_ptr()) == 0
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-# a preceding kernel so the traced launch has a predecessor (as in the graph)
-tasks[0]._step(N.PHASE_ALL & ~N.PHASE_STATS)
+tasks[0]._step(ph)          # a preceding kernel so the traced launch has a predecessor (as in the graph)
 buf.zero_(); torch.cuda.synchronize()
-ev0.record(); tasks[1]._step(N.PHASE_ALL & ~N.PHASE_STATS); ev1.record(); torch.cuda.synchronize()
-print("event time us", ev0.elapsed_time(ev1)*1e3)
-tr = buf.cpu().numpy().reshape(blocks, 8, 4).astype(np.int64)
-t0 = tr[:, :3, 0]; base = t0[t0>0].min()
-def rel(x): return (x - base)/1e3
-start = rel(tr[:,0,0]); issued = rel(tr[:,:3,1]); arrived = rel(tr[:,:3,2]); done = rel(tr[:,:3,3])
-print("resolution check: unique deltas (ns)", np.unique(np.diff(np.sort(tr[:,0,0])))[:8])
+ev0.record(); tasks[1]._step(ph); ev1.record(); torch.cuda.synchronize()
+print("event time us", ev0.elapsed_time(ev1) * 1e3)
+tr = buf.cpu().numpy().reshape(blocks, 8, 4).astype(np.int64)[:, :4, :]
+base = tr[:, 0, 0].min()
+rel = lambda x: (x - base) / 1e3
+start = rel(tr[:, 0, 0]); issued = rel(tr[:, 0, 1]); arrived = rel(tr[:, :, 2]); done = rel(tr[:, :, 3])
 q = lambda a: np.percentile(a, [0, 10, 50, 90, 100]).round(2)
-print("CTA start (us since first)      p0/10/50/90/100:", q(start))
-print("issue done - start, warp0               :", q(issued[:,0]-start))
-print("data arrived - issue done, warp0        :", q(arrived[:,0]-issued[:,0]))
-print("warp0 compute (end - arrived)           :", q(done[:,0]-arrived[:,0]))
-print("obs warps compute (end - arrived)       :", q((done[:,1:3]-arrived[:,1:3]).ravel()))
-print("CTA lifetime (max end - start)          :", q(done.max(axis=1)-start))
-print("kernel span (last end - first start) us :", done.max() - start.min())
-# how many CTAs are alive over time
+print("CTA start (us since first)        p0/10/50/90/100:", q(start))
+print("copies issued - start (warp 0)                   :", q(issued - start))
+print("data arrived - issued (warp 1)                   :", q(arrived[:, 1] - issued))
+for w, name in enumerate(("warp0 frames+rot", "warp1 reward+tail", "warp2 rot", "warp3 rot")):
+    print(f"{name:18s} done - arrived              :", q(done[:, w] - arrived[:, w]))
+print("CTA lifetime (last warp done - start)            :", q(done.max(axis=1) - start))
+print("kernel span (last done - first start) us         :", done.max() - start.min())
 ends = done.max(axis=1)
-for t in np.arange(0, ends.max()+1, 1.0):
-    alive = ((start <= t) & (ends > t)).sum(); started=(start<=t).sum(); fin=(ends<=t).sum()
-    print(f"t={t:5.1f} us alive={alive:5d} started={started:5d} finished={fin:5d}")
-print("---- second-wave CTAs (start > 6 us)")
-late = start > 6.0
-print("count", late.sum())
-print("issue done - start, warp0   :", q((issued[:,0]-start)[late]))
-print("arrived - issue done, warp0 :", q((arrived[:,0]-issued[:,0])[late]))
-print("warp0 compute               :", q((done[:,0]-arrived[:,0])[late]))
-print("obs compute                 :", q((done[:,1:3]-arrived[:,1:3])[late].ravel()))
-print("lifetime                    :", q((done.max(axis=1)-start)[late]))
-vl = start > 11.0
-print("---- very late CTAs (start > 11 us): count", vl.sum())
-if vl.sum() > 0: print("issue:", q((issued[:,0]-start)[vl]), "wait:", q((arrived[:,0]-issued[:,0])[vl]), "w0 compute:", q((done[:,0]-arrived[:,0])[vl]), "obs compute:", q((done[:,1:3]-arrived[:,1:3])[vl].ravel()), "life:", q((done.max(axis=1)-start)[vl]))
-print("per-warp issue-done minus start (all CTAs), warps 0..4 median:", [float(np.median(issued[:,w]-start)) for w in range(3)])
-print("obs warp end - warp0 end median:", float(np.median(done[:,1:3].max(axis=1) - done[:,0])))
+arr = arrived[:, 1]
+edges = np.arange(0, ends.max() + 0.5, 0.5)
+for i in range(len(edges) - 1):
+    a, b = edges[i], edges[i + 1]
+    print(f"{a:5.1f}-{b:5.1f} us  started {((start >= a) & (start < b)).sum():5d}  arrived {((arr >= a) & (arr < b)).sum():5d}"
+          f"  finished {((ends >= a) & (ends < b)).sum():5d}  alive {((start <= a) & (ends > a)).sum():5d}")
