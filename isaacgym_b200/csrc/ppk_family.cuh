@@ -78,7 +78,8 @@ struct FamilyLayout {
 };
 
 // Named barriers (barrier 0 = __syncthreads):
-//   1  heading table ready: warp 0 arrives, warps 2 and 3 wait           (96 threads)
+//   1  heading table ready: warp 0 arrives, warp 3 waits        } one barrier per waiting warp: a waiter must never
+//   3  heading table ready: warp 0 arrives, warp 2 waits        } wait for ANOTHER waiter's arrival
 //   2  pre-reset state read: warp 1 arrives, warp 2 waits before it overwrites the staged rows of resetting envs
 __device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void bar_wait(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
@@ -228,7 +229,8 @@ family_step_kernel(const __grid_constant__ KArgs k, const __grid_constant__ CUte
       hd_s[u * 2] = make_float4(2.0f * (hq.cw * hq.cw) - 1.0f, hq.sz, hq.cw, __int_as_float(so));
       hd_s[u * 2 + 1] = make_float4(r0[0], r0[1], r0[2], __int_as_float(ro));
     }
-    bar_arrive(1, 96);
+    bar_arrive(1, 64);
+    bar_arrive(3, 64);
     __syncwarp();
     if (fast) mbar_wait(bar + 1, 0);
     PPK_STAMP(2);
@@ -238,7 +240,7 @@ family_step_kernel(const __grid_constant__ KArgs k, const __grid_constant__ CUte
     if (!want_obs) return;
     if (fast) mbar_wait(bar + 1, 0);
     PPK_STAMP(2);
-    bar_wait(1, 96);
+    bar_wait(1, 64);
     rotate_bodies(kItW0, kItW0 + kItW3);
     PPK_STAMP(3);
   } else if (warp == 1) {
@@ -462,7 +464,7 @@ family_step_kernel(const __grid_constant__ KArgs k, const __grid_constant__ CUte
       o[D + d] = qd;
     }
     // ---- ball in the heading frame (frames come from warp 0), lane = env --------------------------------
-    bar_wait(1, 96);
+    bar_wait(3, 64);
     if (lane < TILE) {
       const float* my_ball = root_s + le * L::kRootEnv + k.ball * kRow;
       const float bx = my_ball[0], by = my_ball[1], bz = my_ball[2];

@@ -10,7 +10,14 @@ fixture, so it is self-contained) is pushed through the reference's
 /root/reference by `oracle/ref_extract.py`, composed exactly as the class
 wrappers do (`oracle/task_oracle.py`).  The GPU box has no /root/reference;
 there the fixtures are what pins both the oracle and the CUDA path.
+
+`<variant>_step.npz` (a3, tilt, nes, align, adof): the same for one whole `post_physics_step` executed from the
+reference's own METHOD bodies (`oracle/ref_methods.py`: progress += 1 -> compute_reward -> nonzero(reset_buf) ->
+reset_idx / _reset_idx with its host `random.uniform` draws -> compute_observations, ADOF's counter clear included).
+The launch values the reference drew are stored in the rows of `in__reset_ball_vel` (/ `in__reset_ball_pos_yz`) of
+the envs it reset, which is where the fused CUDA step reads them.
 """
+import random
 import os
 import sys
 
@@ -28,9 +35,45 @@ NUM_ENVS = 96
 SEED = 20261018
 
 
+STEP_SEED = 20261019
+
+
+def make_step_fixtures(only):
+    from oracle import ref_methods as M
+    for variant in M.STEP_VARIANTS:
+        if only and variant not in only:
+            continue
+        cfg = CONFIGS[variant]
+        st_in = make_state(cfg, NUM_ENVS, seed=STEP_SEED + cfg.variant_id)
+        st_in["progress_buf"][[3, 40, 77]] = cfg.max_episode_length - 2          # time-outs: every variant resets some envs
+        st = clone_state(st_in)
+        M.bind_step_functions(variant)
+        task = M.make_ref_task(cfg, st)
+        random.seed(STEP_SEED)
+        with ref_extract.quiet():
+            task.post_physics_step()
+        env_ids = st["reset_buf"].nonzero(as_tuple=False).flatten()
+        b = cfg.ball_actor
+        st_in["reset_ball_vel"][env_ids] = st["root_states"][env_ids, b, 7:10]      # what the reference drew
+        if variant == "adof":
+            st_in["reset_ball_pos_yz"][env_ids] = st["root_states"][env_ids, b, 1:3]
+        out = {"in__" + k: v.numpy() for k, v in st_in.items()}
+        for key in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names + cfg.counter_names:
+            out["out__" + key] = st[key].numpy()
+        out["out__reset_actor_indices"] = task.gym.last("set_actor_root_state_tensor_indexed")[2].numpy()
+        path = os.path.join(GOLDEN_DIR, f"{variant}_step.npz")
+        np.savez_compressed(path, **out)
+        print(f"{variant}_step: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), resets={len(env_ids)}")
+
+
 def main():
     assert ref_extract.available(), "needs /root/reference"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    steps_only = "--steps-only" in sys.argv
+    if steps_only:
+        sys.argv.remove("--steps-only")
+        make_step_fixtures(set(sys.argv[1:]))
+        return
     ref = task_oracle.ReferenceImpl()
     torch.set_num_threads(1)
     only = set(sys.argv[1:])
@@ -54,6 +97,7 @@ def main():
         np.savez_compressed(path, **out)
         print(f"{variant}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), "
               f"resets={int(st['reset_buf'].sum())}, mean reward={float(st['rew_buf'].mean()):.4f}")
+    make_step_fixtures(only)
 
 
 if __name__ == "__main__":

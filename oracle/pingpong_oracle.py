@@ -81,6 +81,16 @@ def base_observations(paddle1, paddle2, ball1, ball2):
 # --------------------------------------------------------------------------
 
 
+# Tests set TERM_SCALE to a list: every reward function then appends, per env, the sum of the magnitudes of the
+# terms that entered that env's reward -- the scale the fp32 rounding of the sum lives on (per-env tolerance).
+TERM_SCALE = None
+
+
+def _note_terms(*terms):
+    if TERM_SCALE is not None:
+        TERM_SCALE.append(sum(torch.as_tensor(t).abs().double() for t in terms))
+
+
 def _dist3(a, b):
     return torch.sqrt((a[..., 0] - b[..., 0]) ** 2 + (a[..., 1] - b[..., 1]) ** 2 + (a[..., 2] - b[..., 2]) ** 2)
 
@@ -106,6 +116,7 @@ def base_reward(paddle1, paddle2, ball1, ball2, reset_buf, progress_buf, max_epi
     d1 = _dist3(paddle1[..., 0:3], ball2[..., 0:3])
     d2 = _dist3(paddle2[..., 0:3], ball1[..., 0:3])
     reward = 1.0 / (1.0 + d1 * d1) + 1.0 / (1.0 + d2 * d2)
+    _note_terms(reward)
     z1 = ball1[..., 2]
     ones = torch.ones_like(reset_buf)
     die = torch.where((z1 < 0.1) & (z1 < 0.1), ones, torch.zeros_like(reset_buf))
@@ -124,6 +135,7 @@ def a3_reward(humanoid_root, paddle, pre_ball, ball, dof_force, dof_vel, reset_b
     vel_reward = torch.where(hit, alpha * torch.abs(vx), torch.zeros_like(vx))
     reward = pos_reward + _power_reward(dof_force, dof_vel, power_coefficient) + vel_reward
     missed = bpos[..., 0] < ppos[..., 0] - 1e-3
+    _note_terms(pos_reward, _power_reward(dof_force, dof_vel, power_coefficient), vel_reward, missed * float(penalty))
     reward = torch.where(missed, reward + penalty, reward)
     return reward, _reset_mask(bpos[..., 2], 0.1, progress_buf, reset_buf, max_episode_length, extra_die=missed)
 
@@ -177,6 +189,7 @@ def tilt_reward(humanoid_root, paddle, pre_ball, ball, dof_force, dof_vel, reset
     reward_calculated |= beyond
     over_net = (bx > 1.7) & (bx < 1.8) & outgoing & (by < 0.4) & (by > -0.4) & (bz > 0.98) & (bz < 1.14)
     net_reward = torch.where(over_net, 400, zero)                        # TILT:1226-1244
+    _note_terms(reward, pos_reward, _power_reward(dof_force, dof_vel, power_coefficient), vel_reward, hit_reward, net_reward)
     reward += pos_reward + _power_reward(dof_force, dof_vel, power_coefficient) + vel_reward + hit_reward + net_reward
     return reward, _reset_mask(bz, 0.1, progress_buf, reset_buf, max_episode_length)
 
@@ -198,6 +211,7 @@ def nes_reward(humanoid_root, paddle, pre_ball, ball, dof_force, dof_vel, reset_
                              1.0 * torch.exp(-20.0 * dist * dist), zero)  # NES:1188-1195
     vel_reward = torch.where(hit & ~paddle_condition_calculated, alpha * torch.abs(vx), zero)
     paddle_condition_calculated |= hit
+    _note_terms(reward, pos_reward, _power_reward(dof_force, dof_vel, power_coefficient), vel_reward, (bpos[..., 2] < 0.1) * 800.0)
     reward += pos_reward + _power_reward(dof_force, dof_vel, power_coefficient) + vel_reward
     reward = torch.where(bpos[..., 2] < 0.1, -800 + reward, reward)       # NES:1313-1315
     return reward, _reset_mask(bpos[..., 2], 0.1, progress_buf, reset_buf, max_episode_length, early_stop=False)
@@ -230,6 +244,7 @@ def align_reward(humanoid_root, paddle, pre_ball, ball, dof_force, dof_vel, rese
     reward_calculated |= bx >= 3.1
     reward = pos_reward + _power_reward(dof_force, dof_vel, power_coefficient) + vel_reward + hit_reward
     missed = bx < humanoid_root[..., 0] - 0.05
+    _note_terms(pos_reward, _power_reward(dof_force, dof_vel, power_coefficient), vel_reward, hit_reward, missed * float(penalty))
     reward = torch.where(missed, reward + penalty, reward)
     return reward, _reset_mask(bpos[..., 2], 0.1, progress_buf, reset_buf, max_episode_length)
 
@@ -262,6 +277,8 @@ def align2_reward(h1_root, paddle1, h2_root, paddle2, pre_ball, ball, dof_force,
     power_reward = _power_reward(dof_force, dof_vel, power_coefficient)
     r1 = pos1 + power_reward + vel1 + hit1
     r2 = pos2 + power_reward + vel2 + hit2
+    _note_terms(pos1, power_reward, vel1, hit1, (bx < h1_root[..., 0] - 0.05) * float(penalty))
+    _note_terms(pos2, power_reward, vel2, hit2, (bx > h2_root[..., 0] + 0.05) * float(penalty))
     r1 = torch.where(bx < h1_root[..., 0] - 0.05, r1 + penalty, r1)
     r2 = torch.where(bx > h2_root[..., 0] + 0.05, r2 + penalty, r2)
     reset = _reset_mask(bpos[..., 2], 0.1, progress_buf, reset_buf, max_episode_length)
@@ -354,6 +371,7 @@ def adof_reward(humanoid_root, pelvis, paddle, pre_ball, ball, dof_force, dof_ve
     die_penalty = torch.where(low & ~die_penalty_calculated & ~humanoid_die_calculated, die_penalty_float, zero)
     die_penalty_calculated |= low
     humanoid_die_calculated |= (pelvis_height < 0.97)
+    _note_terms(pos_reward, power_reward, vel_reward, table, net, die_penalty, time_penalty, ref_reward)
     reward = zero + (pos_reward + power_reward + vel_reward + table + net + die_penalty + time_penalty + ref_reward)
     reset = _reset_mask(bz, 0.78, progress_buf, reset_buf, max_episode_length, early_stop=False)
     return (reward, reset, paddle_condition_calculated, hit_table_calculated, die_penalty_calculated,

@@ -7,7 +7,7 @@ obs / reward fp32 -- rtol 1e-5 (+ small atol), per field, see helpers.assert_clo
 import pytest
 import torch
 
-from helpers import VARIANTS, assert_close_fields, load_golden
+from helpers import STEP_VARIANTS, VARIANTS, assert_close_fields as _assert_close_fields, load_golden, oracle_step_with_term_scale
 from isaacgym_b200 import _native as N
 from isaacgym_b200.config import CONFIGS
 from isaacgym_b200.synth import clone_state, make_state
@@ -33,6 +33,17 @@ def run(cfg, g, phases):
     torch.cuda.synchronize()
 
 
+def assert_close_fields(cfg, got_obs, want_obs, got_rew, want_rew, context="", rew_scale=None):
+    _assert_close_fields(cfg, got_obs, want_obs, got_rew, want_rew, context, rew_scale=rew_scale)
+
+
+def check_fields(cfg, g, want, context):
+    """obs / reward of the CUDA path against an oracle state produced by `oracle_full_step` (which also recorded,
+    per env, the magnitude of the terms that entered the reward: the per-env absolute tolerance)."""
+    _assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], context,
+                         rew_scale=want.get("_rew_scale"))
+
+
 def assert_exact(cfg, g, want, names, context):
     for name in names:
         a, b = g[name].cpu(), want[name]
@@ -49,24 +60,33 @@ def test_golden_vectors(variant):
         run(cfg, g, N.PHASE_REWARD | N.PHASE_OBS)
     else:
         run(cfg, g, N.PHASE_PROGRESS | N.PHASE_REWARD | N.PHASE_OBS)
-    assert_close_fields(cfg, g["obs_buf"], outs["obs_buf"], g["rew_buf"], outs["rew_buf"], f"golden[{variant}]")
+    # the fixtures carry no term breakdown: the oracle on the same inputs says which terms entered each env's reward
+    o = clone_state(ins)
+    if variant != "base":
+        o["progress_buf"] += 1
+    _, scale = oracle_step_with_term_scale(cfg, o, lambda c, s_: task_oracle.compute_reward(c, s_))
+    assert_close_fields(cfg, g["obs_buf"], outs["obs_buf"], g["rew_buf"], outs["rew_buf"], f"golden[{variant}]", rew_scale=scale)
     assert torch.equal(g["reset_buf"].cpu(), outs["reset_buf"])
     assert_exact(cfg, g, outs, cfg.flag_names + cfg.counter_names + cfg.state_names, f"golden[{variant}]")
 
 
 def oracle_full_step(cfg, st):
     o = clone_state(st)
-    if cfg.variant == "base":
-        from oracle import pingpong_oracle as O
-        o["progress_buf"] += 1
-        ids = o["reset_buf"].nonzero(as_tuple=False).flatten()
-        if len(ids) > 0:
-            O.base_reset_idx(o, ids, o["reset_ball_vel"][0], o["reset_ball_vel"][1])
-        o["obs_buf"][:] = task_oracle.compute_observations(cfg, o)
-        task_oracle.compute_reward(cfg, o)
-        stats = task_oracle.step_stats(cfg, o)
-    else:
-        _, _, stats = task_oracle.post_physics_step(cfg, o)
+
+    def step(cfg, o):
+        if cfg.variant == "base":
+            from oracle import pingpong_oracle as O
+            o["progress_buf"] += 1
+            ids = o["reset_buf"].nonzero(as_tuple=False).flatten()
+            if len(ids) > 0:
+                O.base_reset_idx(o, ids, o["reset_ball_vel"][0], o["reset_ball_vel"][1])
+            o["obs_buf"][:] = task_oracle.compute_observations(cfg, o)
+            task_oracle.compute_reward(cfg, o)
+            return task_oracle.step_stats(cfg, o)
+        return task_oracle.post_physics_step(cfg, o)[2]
+
+    stats, scale = oracle_step_with_term_scale(cfg, o, step)
+    o["_rew_scale"] = scale
     return o, stats
 
 
@@ -86,7 +106,7 @@ def test_fused_step_matches_oracle(variant, n, seed):
     run(cfg, g, N.PHASE_ALL)
     ctx = f"{variant} n={n}"
     assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, ctx)
-    assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], ctx)
+    check_fields(cfg, g, want, ctx)
     # statistics: fp64 partial sums on the device vs fp64 oracle sums
     got = g["stats"].sum(dim=0).cpu()
     rs = stats["reward_sum"]
@@ -148,7 +168,7 @@ def test_multi_step_trajectory(variant):
             r[:, b, 0:3] += 0.05 * r[:, b, 7:10]
             r[:, b, 7:10] += dvd
             r[:, b, 7] = torch.where(flipd, -r[:, b, 7], r[:, b, 7])
-        task_oracle.post_physics_step(cfg, o)
+        _, scale = oracle_step_with_term_scale(cfg, o, lambda c, s_: task_oracle.post_physics_step(c, s_))
         task.post_physics_step()
         torch.cuda.synchronize()
         ctx = f"{variant} step {step}"
@@ -156,7 +176,7 @@ def test_multi_step_trajectory(variant):
             assert torch.equal(getattr(task, name).cpu(), o[name]), f"{ctx}: {name}"
         assert torch.equal(task.root_states.cpu(), o["root_states"]), ctx
         assert torch.equal(task.vec_dof_states.cpu(), o["dof_states"]), ctx
-        assert_close_fields(cfg, task.obs_buf, o["obs_buf"], task.rew_buf, o["rew_buf"], ctx)
+        assert_close_fields(cfg, task.obs_buf, o["obs_buf"], task.rew_buf, o["rew_buf"], ctx, rew_scale=scale)
 
 
 @pytest.mark.parametrize("variant", ["tilt", "a4", "adof", "base"])
@@ -187,7 +207,7 @@ def test_ragged_sizes(variant, n):
         ok = bool(tail.all()) if big.dtype == torch.bool else bool((tail == -777).all())
         assert ok, f"{variant} n={n}: {name} was written past its end"
     assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, f"{variant} n={n}")
-    assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], f"{variant} n={n}")
+    check_fields(cfg, g, want, f"{variant} n={n}")
 
 
 def test_empty_batch_is_a_no_op():
@@ -234,7 +254,8 @@ def test_pre_ball_clone_layouts_agree():
         t.pre_physics_step(act)
         t.post_physics_step()
     torch.cuda.synchronize()
-    assert torch.equal(a.pre_ball2_root_states, a.root_states[:, cfg.ball_actor, :].clone()) or True
+    # the full clone holds the ball row as it was when pre_physics_step ran (TILT:1020), the compact one its vx, vz
+    assert torch.equal(a.pre_ball2_root_states[:, [7, 9]], b.pre_ball2_root_states)
     assert torch.equal(a.rew_buf, b.rew_buf) and torch.equal(a.obs_buf, b.obs_buf) and torch.equal(a.reset_buf, b.reset_buf)
 
 
@@ -344,7 +365,7 @@ def test_adof_compact_reference_pose(n):
     for name in ("obs_buf", "rew_buf") + STATE_EXACT + cfg.flag_names + cfg.counter_names:
         assert torch.equal(comp[name], full[name]), name
     assert_exact(cfg, comp, want, STATE_EXACT + cfg.flag_names + cfg.counter_names, f"adof compact n={n}")
-    assert_close_fields(cfg, comp["obs_buf"], want["obs_buf"], comp["rew_buf"], want["rew_buf"], f"adof compact n={n}")
+    check_fields(cfg, comp, want, f"adof compact n={n}")
 
 
 @pytest.mark.parametrize("variant,n", [("tilt", 65536), ("a4", 65536), ("adof", 32768)])
@@ -413,7 +434,7 @@ def test_randomised_coefficients(variant, seed):
     run(cfg, g, N.PHASE_ALL)
     ctx = f"{variant} random coefficients #{seed}"
     assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, ctx)
-    assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], ctx)
+    check_fields(cfg, g, want, ctx)
 
 
 @pytest.mark.parametrize("variant", ["tilt", "nes", "a4"])
@@ -433,7 +454,7 @@ def test_scattered_body_ids_take_the_generic_staging_path(variant):
     run(cfg, g, N.PHASE_ALL)
     ctx = f"{variant} scattered ids"
     assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, ctx)
-    assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], ctx)
+    check_fields(cfg, g, want, ctx)
 
 
 @pytest.mark.parametrize("variant", ["tilt", "adof", "a4"])
@@ -455,7 +476,7 @@ def test_tensors_that_are_only_4_byte_aligned(variant):
     run(cfg, g, N.PHASE_ALL)
     ctx = f"{variant} misaligned"
     assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, ctx)
-    assert_close_fields(cfg, g["obs_buf"], want["obs_buf"], g["rew_buf"], want["rew_buf"], ctx)
+    check_fields(cfg, g, want, ctx)
 
 
 def test_host_session_full_size_tilt():
@@ -476,3 +497,124 @@ def test_host_session_full_size_tilt():
                 assert torch.equal(sess.state[name], dev[name].cpu()), f"step {step}: {name}"
     finally:
         sess.close()
+
+
+# ---- BASELINE.json's own sizes against the oracle (the port needs well under a second per config) -----------------
+
+@pytest.mark.parametrize("variant,n,with_pre", [("a3", 16384, False), ("tilt", 65536, False), ("a4", 65536, False),
+                                                ("adof", 32768, False), ("align", 131072, True), ("nes", 65536, False),
+                                                ("align2", 65536, False), ("base", 4096, False)])
+def test_baseline_sizes_match_oracle(variant, n, with_pre):
+    """configs[0..4] of BASELINE.json at their full per-GPU sizes: the fused step (ALIGN: pre_physics_step + step,
+    the "full task step" of configs[4]) against the oracle on the same seeded inputs, every env compared."""
+    cfg = CONFIGS[variant]
+    st = make_state(cfg, n, seed=1000 * cfg.variant_id + 5, adversarial=True)
+    if variant == "base":
+        st["reset_buf"] = (torch.rand(n, generator=torch.Generator().manual_seed(11)) < 0.1).to(torch.int64)
+        st["reset_ball_vel"] = st["reset_ball_vel"][:2].contiguous()
+    o_in = clone_state(st)
+    g = gpu_state(st)
+    if with_pre:
+        task_oracle.pre_physics_step(cfg, o_in)            # pd targets + the ball row clone the reward reads
+        lib = N.load()
+        N.check(lib.ppk_pre_physics_step(N.make_task(cfg), N.make_buffers(cfg, g), N.current_stream_ptr()), "pre")
+        torch.testing.assert_close(g["pd_targets"].cpu(), o_in["pd_targets"], rtol=1e-6, atol=1e-7)
+        assert torch.equal(g["pre_ball_states"].cpu(), o_in["pre_ball_states"])
+    want, stats = oracle_full_step(cfg, o_in)
+    run(cfg, g, N.PHASE_ALL)
+    ctx = f"{variant} n={n} (BASELINE size)"
+    assert_exact(cfg, g, want, STATE_EXACT + cfg.flag_names + cfg.counter_names + cfg.state_names, ctx)
+    check_fields(cfg, g, want, ctx)
+    got = g["stats"].sum(dim=0).cpu()
+    assert float(got[1]) == float(stats["progress_sum"]) and float(got[2]) == float(stats["reset_count"])
+
+
+def test_adof_has_fallen_at_the_threshold():
+    """ADOF's `has_fallen` compares a MEAN of 23 fp32 norms with 0.32 (ADOF:1412): the only flag of the path that
+    hangs on a reduction.  Every env here is planted so that the mean lands within a few ulp of 0.32.  Where the
+    fp64 value of the same fp32 inputs is more than 2 ulp(0.32) away from the threshold every fp32 summation order
+    gives the same answer: the kernel (shuffle tree) must agree with the oracle (ATen's CPU order) exactly.  Inside
+    +-2 ulp the reference's own answer depends on the reduction order of the ATen build it runs on (CPU vector ISA,
+    or the CUDA reduce kernel in production), so either answer is the reference's: those envs are only counted."""
+    cfg = CONFIGS["adof"]
+    n = 8192
+    st = make_state(cfg, n, seed=4321, adversarial=False)
+    bal = torch.tensor(cfg.balance_ids)
+    gen = torch.Generator().manual_seed(99)
+    ref = st["initial_body_states"][:, bal, 0:3].double()
+    d = torch.randn(n, len(bal), 3, generator=gen, dtype=torch.float64)
+    ulp = 2.0 ** -25                                          # ulp of fp32 in [0.25, 0.5)
+    aim = 0.32 + (torch.rand(n, generator=gen, dtype=torch.float64) * 32.0 - 16.0) * ulp     # +-16 ulp around 0.32
+    d = d * (aim / d.norm(dim=-1).mean(dim=-1))[:, None, None]
+    st["rigid_body_states"][:, bal, 0:3] = (ref + d).float()
+    for name in cfg.counter_names:
+        st[name][:] = False
+    cur = st["rigid_body_states"][:, bal, 0:3]
+    exact = (cur.double() - st["initial_body_states"][:, bal, 0:3].double()).norm(dim=-1).mean(dim=-1)
+    margin = (exact - float(torch.tensor(0.32, dtype=torch.float32))) / ulp
+    assert int((margin.abs() < 2).sum()) > n // 40 and int((margin.abs() > 2).sum()) > n // 2, "the planted batch does not straddle the threshold"
+    want, _ = oracle_full_step(cfg, st)
+    g = gpu_state(st)
+    run(cfg, g, N.PHASE_ALL)
+    got_fall, want_fall = g["fall_down_count"].cpu(), want["fall_down_count"]
+    clear = margin.abs() > 2.0
+    assert torch.equal(got_fall[clear], want_fall[clear]), "has_fallen differs where no fp32 summation order can flip it"
+    assert torch.equal(want_fall[clear], (margin > 0)[clear])
+    flips = int((got_fall != want_fall)[~clear].sum())
+    print(f"has_fallen: {int((~clear).sum())} envs within 2 ulp of 0.32, {flips} of them decided differently by the two summation orders")
+    # everything else of those envs is still compared, with the envs whose flag legitimately differs left out
+    same = got_fall == want_fall
+    for name in STATE_EXACT + cfg.flag_names:
+        assert torch.equal(g[name].cpu()[same], want[name][same]), name
+    _assert_close_fields(cfg, g["obs_buf"].cpu()[same], want["obs_buf"][same], g["rew_buf"].cpu()[same], want["rew_buf"][same],
+                         "adof threshold batch", rew_scale=want["_rew_scale"][same])
+
+
+@pytest.mark.parametrize("variant", ["tilt", "a4", "adof", "base"])
+def test_fused_observation_clamp(variant):
+    """VecTask.step's `clamp(obs_buf, -clipObservations, clipObservations)` happens inside the step kernels
+    (PpkBuffers.clip_observations); 0 / inf = upstream's default, no clamp."""
+    cfg = CONFIGS[variant]
+    n = 1500
+    st = make_state(cfg, n, seed=8)
+    if variant == "base":
+        st["reset_ball_vel"] = st["reset_ball_vel"][:2].contiguous()
+    plain = gpu_state(st)
+    run(cfg, plain, N.PHASE_ALL)
+    assert float(plain["obs_buf"].abs().max()) > 1.5          # the clamp has something to do
+    clipped = gpu_state(st)
+    clipped["clip_observations"] = 1.5
+    run(cfg, clipped, N.PHASE_ALL)
+    assert torch.equal(clipped["obs_buf"], plain["obs_buf"].clamp(-1.5, 1.5))
+    for name in ("rew_buf", "reset_buf", "progress_buf"):
+        assert torch.equal(clipped[name], plain[name]), name
+    inf = gpu_state(st)
+    inf["clip_observations"] = float("inf")
+    run(cfg, inf, N.PHASE_ALL)
+    assert torch.equal(inf["obs_buf"], plain["obs_buf"])
+
+
+@pytest.mark.parametrize("variant", STEP_VARIANTS)
+def test_golden_step_fixture(variant):
+    """One whole post_physics_step frozen from the reference's own METHOD bodies (oracle/ref_methods.py, made by
+    oracle/make_golden.py): the fused kernel -- reset rows, progress, flags, counters bit-exact; obs / reward per field."""
+    cfg = CONFIGS[variant]
+    ins, outs = load_golden(variant, step=True)
+    g = gpu_state(ins)
+    g["actor_indices"], g["dof_indices"] = ins["actor_indices"].to(DEV), ins["dof_indices"].to(DEV)
+    n = ins["progress_buf"].shape[0]
+    g["reset_count"] = torch.zeros(1, dtype=torch.int32, device=DEV)
+    g["reset_actor_indices"] = torch.zeros(n * cfg.num_actors, dtype=torch.int32, device=DEV)
+    g["reset_dof_indices"] = torch.zeros(n, dtype=torch.int32, device=DEV)
+    run(cfg, g, N.PHASE_ALL)
+    ctx = f"golden step[{variant}]"
+    exact = ("reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names + cfg.counter_names
+    assert_exact(cfg, g, outs, exact, ctx)
+    o = clone_state(ins)
+    _, scale = oracle_step_with_term_scale(cfg, o, lambda c, s_: task_oracle.post_physics_step(c, s_))
+    assert_close_fields(cfg, g["obs_buf"], outs["obs_buf"], g["rew_buf"], outs["rew_buf"], ctx, rew_scale=scale)
+    # the compacted int32 actor index list the gym setter takes (TILT:876-883); env order within it is unspecified
+    k = int(g["reset_count"].item())
+    got = g["reset_actor_indices"][:k * cfg.num_actors].cpu().view(k, cfg.num_actors)
+    want = outs["reset_actor_indices"].view(-1, cfg.num_actors)
+    assert k == want.shape[0] and torch.equal(got[got[:, 0].argsort()], want[want[:, 0].argsort()])

@@ -6,7 +6,7 @@ import math
 import pytest
 import torch
 
-from helpers import VARIANTS, load_golden
+from helpers import STEP_VARIANTS, VARIANTS, load_golden
 from isaacgym_b200.config import CONFIGS
 from isaacgym_b200.synth import clone_state, make_state
 from oracle import jit_utils_restated as J
@@ -195,3 +195,21 @@ def test_first_layer_restatement_equals_torch_autocast():
             # identical up to fp32 summation order: at most one fp16 ulp, on a small fraction of entries
             assert float(((a - t).abs() > 2.0 ** -10 * t.abs() + 1e-7).float().mean()) == 0.0
             assert float((a != t).float().mean()) < 0.01
+
+
+@pytest.mark.parametrize("variant", STEP_VARIANTS)
+def test_oracle_step_matches_reference_method_fixture(variant):
+    """tests/golden/<variant>_step.npz: one whole post_physics_step executed from the reference's own class-method
+    text (reward -> nonzero -> _reset_idx -> observations).  The restated step reproduces every buffer bit for bit."""
+    from isaacgym_b200.config import CONFIGS
+    from oracle import task_oracle
+    cfg = CONFIGS[variant]
+    ins, outs = load_golden(variant, step=True)
+    st = {k: v.clone() for k, v in ins.items()}
+    env_ids, idx, _ = task_oracle.post_physics_step(cfg, st)
+    assert len(env_ids) > 0
+    for key, want in outs.items():
+        if key == "reset_actor_indices":
+            assert torch.equal(idx[0], want)
+        else:
+            assert torch.equal(st[key], want), (variant, key)
