@@ -252,6 +252,11 @@ PPK_API int ppk_stats_reduce(double* stats, double* out, void* stream);
 typedef struct PpkHostSession PpkHostSession;
 PPK_API int ppk_host_session_create(const PpkTask* task, int64_t max_envs, int32_t num_chunks, PpkHostSession** out);
 PPK_API int ppk_host_session_destroy(PpkHostSession* s);
+/* `host_buf->reset_ball_vel` / `reset_ball_pos_yz` are per-step inputs: they are read (in place when pinned, else
+ * copied per chunk) by every call that includes PPK_PHASE_RESET, so refilling them in place between calls gives every
+ * reset a fresh draw (TILT:857-862).  The initial_* tensors are uploaded when their pointers or num_envs change.
+ * With PPK_PHASE_STATS `host_buf->stats` is a HOST array of PPK_NUM_STATS doubles that receives the sums of this
+ * call (PpkStat order; divide by N); the session's device slots are cleared by it. */
 PPK_API int ppk_host_post_physics_step(PpkHostSession* s, const PpkBuffers* host_buf, uint32_t phases);
 /* bytes moved by the last call */
 PPK_API int ppk_host_session_traffic(const PpkHostSession* s, int64_t* h2d_bytes, int64_t* d2h_bytes);

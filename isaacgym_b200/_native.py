@@ -74,14 +74,21 @@ def lib_path() -> str:
 
 
 def load():
-    """Load libppk.so (building it first if the sources are newer).  Raises if unavailable."""
+    """Load libppk.so.  Where the sources and nvcc are present (the build container, the GPU box) the library is
+    rebuilt first whenever its recorded source hash differs from the sources -- a stale binary is never loaded
+    silently; `build()` returns at once when the hash matches.  PPK_LIB loads another build as is.  Raises if
+    unavailable."""
     global _LIB
     if _LIB is not None:
         return _LIB
     path = lib_path()
-    if not os.path.exists(path):
-        from . import build as _build     # nvcc is present in the image; on the GPU box the .so travels
-        _build.build()
+    if not os.environ.get("PPK_LIB"):
+        from . import build as _build
+        if os.path.isdir(_build.CSRC) and (os.path.exists(_build.nvcc_path()) or not os.path.exists(path)):
+            _build.build()
+        elif os.path.isdir(_build.CSRC) and not _build.stamp_matches():
+            raise RuntimeError(f"{path} was built from other sources than isaacgym_b200/csrc (hash mismatch) and nvcc "
+                               "is not available to rebuild it: run `python -m isaacgym_b200.build` where nvcc is")
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: the CUDA extension is the only implementation of the "
                            "ping-pong task step (no CPU fallback). Run `python -m isaacgym_b200.build`.")

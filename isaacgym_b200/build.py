@@ -37,13 +37,21 @@ def _source_hash():
     return h.hexdigest()
 
 
+def nvcc_path():
+    return os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+def stamp_matches():
+    return os.path.exists(LIB_PATH) and os.path.exists(STAMP) and open(STAMP).read().strip() == _source_hash()
+
+
 def build(force=False, verbose=False, out=None):
     """`out`: build a variant (PPK_NVCC_EXTRA) somewhere else, e.g. scratch/libs/x.so for A/B runs with PPK_LIB."""
     os.makedirs(LIB_DIR, exist_ok=True)
     want = _source_hash()
     if out is None and not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP) and open(STAMP).read().strip() == want:
         return LIB_PATH
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    nvcc = nvcc_path()
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB_PATH] + srcs
     if verbose:

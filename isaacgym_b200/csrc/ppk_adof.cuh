@@ -20,6 +20,8 @@
 //              time-out mask, predicated reset (ADOF:965-1028); then the dof / ball / reference-dof
 //              segments of the obs row, lane = element.
 #pragma once
+#include <stdlib.h>
+
 #include "ppk_async.cuh"
 #include "ppk_device.cuh"
 
@@ -114,6 +116,12 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
       mbar_fence_init();
     }
     __syncthreads();
+    // soft start of the first wave (see ppk_family.cuh): CTA b delays its copies by (b / #SMs) * stagger cycles
+    if (k.stagger > 0 && (int)blockIdx.x < k.first_wave && (int)blockIdx.x >= k.num_sms) {
+      const long long wait = (long long)((int)blockIdx.x / k.num_sms) * k.stagger;
+      const long long t0 = clock64();
+      while (clock64() - t0 < wait) __nanosleep(64);
+    }
     if (threadIdx.x == 0) {
       mbar_arrive_expect_tx(bar, L::kTxBytes);
       bulk_g2s(root_s, k.root + (size_t)env0 * L::kRoot, 4u * T * L::kRoot, bar);
@@ -464,6 +472,27 @@ inline int launch_adof(const KArgs& k0, cudaStream_t s) {
     return PPK_ERR_LAUNCH;
   const bool fused_reset = (k.phases & PPK_PHASE_RESET) != 0 && !(k.phases & kPhaseDeferCounterClear);
   const long long tiles = (k.n + kAdofTile - 1) / kAdofTile;
+  {
+    static int occ_c = 0, occ_f = 0, sms = 0;
+    int& occ = compact ? occ_c : occ_f;
+    if (occ == 0) {
+      int dev = 0, o = 0, n_sm = 0;
+      const bool ok = cudaGetDevice(&dev) == cudaSuccess &&
+                      (compact ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, adof_step_kernel<true>, kAdofThreads, smem)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, adof_step_kernel<false>, kAdofThreads, smem)) == cudaSuccess &&
+                      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && o > 0 && n_sm > 0;
+      if (ok) { occ = o; sms = n_sm; } else cudaGetLastError();
+    }
+    static int stag = -1;
+    if (stag < 0) {
+      const char* e = getenv("PPK_STAGGER_ADOF");
+      stag = e ? atoi(e) : 600;
+      if (stag < 0) stag = 0;
+    }
+    k.num_sms = sms > 0 ? sms : 1;
+    k.first_wave = occ * sms;
+    k.stagger = (occ > 0 && tiles > (long long)occ * sms) ? stag : 0;
+  }
   if (compact) adof_step_kernel<true><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
   else adof_step_kernel<false><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
   if (cudaGetLastError() != cudaSuccess) return PPK_ERR_LAUNCH;

@@ -122,36 +122,39 @@ family_step_kernel(const __grid_constant__ KArgs k, const __grid_constant__ CUte
   // ---- stage ---------------------------------------------------------------------------------------
   PPK_STAMP(0);
   if (fast) {
-    if (tid == 0) {
-      mbar_init(bar, 1);
-      mbar_init(bar + 1, 1);
-      mbar_fence_init();
+    if (warp == 0) {
+      // one elected lane of the converged warp 0 sets the barriers up and issues the seven copies (warp-uniform
+      // operands: no per-lane serialisation); the other warps meet it at the __syncthreads below
+      if (elect_one()) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_fence_init();
+        if (k.stagger > 0 && (int)blockIdx.x < k.first_wave && (int)blockIdx.x >= k.num_sms) {
+          const long long wait = (long long)((int)blockIdx.x / k.num_sms) * k.stagger;
+          const long long t0 = clock64();
+          while (clock64() - t0 < wait) __nanosleep(64);
+        }
+        const int p0 = (int)(env0 >> 1);
+        // the heading frames need only row ids[0]: requested first, on their own barrier, so that warp 0 computes
+        // them (atan2f / sinf / cosf: ~0.6 us) while the rest of the tile is still in flight
+        mbar_arrive_expect_tx(bar, 4u * L::kUnits * r0s);
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) tma_load_2d(row0_s + (h * 2 + q) * L::kPairs * r0s, &m_row0, k.row0_c[h][q], p0, bar);
+        mbar_arrive_expect_tx(bar + 1, 4u * L::kUnits * L::kSpanF + L::kLinearTx);
+        bulk_g2s(root_s, k.root + (size_t)env0 * L::kRootEnv, 4u * TILE * L::kRootEnv, bar + 1);
+        bulk_g2s(dof_s, k.dof + (size_t)env0 * 2 * D, 4u * TILE * 2 * D, bar + 1);
+        bulk_g2s(force_s, k.force + (size_t)env0 * D, 4u * TILE * D, bar + 1);
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            tma_load_2d(span_s + (h * 2 + q) * L::kPairs * L::kSpanF, &m_span, k.span_c[h][q], p0, bar + 1);
+      }
+      __syncwarp();
     }
     __syncthreads();        // the initialised barriers are visible to every waiter
-    if (tid == 0) {
-      if (k.stagger > 0 && (int)blockIdx.x < k.first_wave && (int)blockIdx.x >= k.num_sms) {
-        const long long wait = (long long)((int)blockIdx.x / k.num_sms) * k.stagger;
-        const long long t0 = clock64();
-        while (clock64() - t0 < wait) __nanosleep(64);
-      }
-      const int p0 = (int)(env0 >> 1);
-      // the heading frames need only row ids[0]: requested first, on their own barrier, so that warp 0 computes
-      // them (atan2f / sinf / cosf: ~0.6 us) while the rest of the tile is still in flight
-      mbar_arrive_expect_tx(bar, 4u * L::kUnits * r0s);
-#pragma unroll
-      for (int h = 0; h < H; ++h)
-#pragma unroll
-        for (int q = 0; q < 2; ++q) tma_load_2d(row0_s + (h * 2 + q) * L::kPairs * r0s, &m_row0, k.row0_c[h][q], p0, bar);
-      mbar_arrive_expect_tx(bar + 1, 4u * L::kUnits * L::kSpanF + L::kLinearTx);
-      bulk_g2s(root_s, k.root + (size_t)env0 * L::kRootEnv, 4u * TILE * L::kRootEnv, bar + 1);
-      bulk_g2s(dof_s, k.dof + (size_t)env0 * 2 * D, 4u * TILE * 2 * D, bar + 1);
-      bulk_g2s(force_s, k.force + (size_t)env0 * D, 4u * TILE * D, bar + 1);
-#pragma unroll
-      for (int h = 0; h < H; ++h)
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-          tma_load_2d(span_s + (h * 2 + q) * L::kPairs * L::kSpanF, &m_span, k.span_c[h][q], p0, bar + 1);
-    }
   } else {
     // generic path (tail tile, unaligned tensors, non-consecutive ids): plain loads, same layout
     const int env_stride = k.B * kRow;
@@ -213,8 +216,11 @@ family_step_kernel(const __grid_constant__ KArgs k, const __grid_constant__ CUte
     }
   };
   constexpr int kIters = (L::kUnits * J + 31) / 32;      // 10
-  constexpr int kItW0 = (kIters * 2 + 2) / 5;            // 4: warp 0 (its frames are ready before the data)
-  constexpr int kItW3 = (kIters * 2 + 2) / 5;            // 4: warp 3
+#ifndef PPK_ROT_W0
+#define PPK_ROT_W0 ((kIters * 2 + 2) / 5)
+#endif
+  constexpr int kItW0 = PPK_ROT_W0;                      // warp 0 (its frames are ready before the data)
+  constexpr int kItW3 = PPK_ROT_W0;                      // warp 3; warp 2 takes the rest after the reset / tail
   static_assert(kItW0 + kItW3 <= kIters, "rotation split");   // warp 2 takes the rest after the reset / tail
 
   if (warp == 0) {

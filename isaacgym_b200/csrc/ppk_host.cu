@@ -48,8 +48,11 @@ struct PpkHostSession {
   double* stats = nullptr;
   uint32_t* scratch = nullptr;
   bool constants_uploaded = false;
-  const void* const_src[5] = {};
+  const void* const_src[3] = {};
+  int64_t const_n = 0;
+  double* stats_out = nullptr;     // [PPK_NUM_STATS] reduced on the device, copied to the caller's host `stats`
   bool zero_copy = false;   // small per-env buffers are pinned host memory: the kernel reads/writes them in place
+  bool zc_launch = false;   // the launch table (reset_ball_vel / reset_ball_pos_yz) is pinned: read in place
   int64_t h2d_bytes = 0, d2h_bytes = 0;
   // recorded pipeline
   PpkBuffers key;
@@ -146,6 +149,12 @@ int enqueue_step(PpkHostSession* s, const PpkBuffers* hb, uint32_t phases) {
   const bool zc_rows = zc && v != PPK_BASE;          // ... and writes reset rows straight to the host tensors
   cudaStream_t origin = s->streams[0];
   if (adof_deferred) CU(cudaMemsetAsync(s->scratch, 0, sizeof(uint32_t), origin));
+  // The launch table is the step's per-call INPUT (the caller refills it in place whenever it wants fresh draws,
+  // TILT:857-862 draws per reset): it travels with every step that may reset, never cached.  BASE: one pair for all.
+  if (rst && v == PPK_BASE && !s->zc_launch) {
+    CU(cudaMemcpyAsync(s->reset_vel, hb->reset_ball_vel, sizeof(float) * 6, cudaMemcpyHostToDevice, origin));
+    s->h2d_bytes += sizeof(float) * 6;
+  }
   CU(cudaEventRecord(s->ev_fork, origin));
   for (int i = 1; i < kStreams; ++i) CU(cudaStreamWaitEvent(s->streams[i], s->ev_fork, 0));
 
@@ -179,6 +188,14 @@ int enqueue_step(PpkHostSession* s, const PpkBuffers* hb, uint32_t phases) {
     if (v == PPK_ALIGN2 && rew) {
       if (!zc) CU(cudaMemcpyAsync(s->last_hitter + lo, hb->last_hitter + lo, sizeof(int64_t) * m, cudaMemcpyHostToDevice, st));
       s->h2d_bytes += sizeof(int64_t) * m;
+    }
+    if (rst && v != PPK_BASE && !s->zc_launch) {
+      CU(cudaMemcpyAsync(s->reset_vel + (size_t)lo * 3, hb->reset_ball_vel + (size_t)lo * 3, sizeof(float) * m * 3, cudaMemcpyHostToDevice, st));
+      s->h2d_bytes += sizeof(float) * m * 3;
+      if (v == PPK_ADOF) {
+        CU(cudaMemcpyAsync(s->reset_yz + (size_t)lo * 2, hb->reset_ball_pos_yz + (size_t)lo * 2, sizeof(float) * m * 2, cudaMemcpyHostToDevice, st));
+        s->h2d_bytes += sizeof(float) * m * 2;
+      }
     }
 
     // ---- the fused step on the chunk
@@ -216,6 +233,10 @@ int enqueue_step(PpkHostSession* s, const PpkBuffers* hb, uint32_t phases) {
     if (zc_rows) {
       db.root_states_out = hb->root_states + (size_t)lo * A * kRow;
       db.dof_states_out = hb->dof_states + (size_t)lo * D * 2;
+    }
+    if (rst && s->zc_launch) {      // pinned launch table: only the rows of resetting envs are read, in place
+      db.reset_ball_vel = (v == PPK_BASE) ? hb->reset_ball_vel : hb->reset_ball_vel + (size_t)lo * 3;
+      if (hb->reset_ball_pos_yz) db.reset_ball_pos_yz = hb->reset_ball_pos_yz + (size_t)lo * 2;
     }
     int rc = ppk_post_physics_step(&s->dev_task, &db, phases | (adof_deferred ? kDeferCounterClear : 0u), st);
     if (rc != PPK_OK) return rc;
@@ -255,6 +276,13 @@ int enqueue_step(PpkHostSession* s, const PpkBuffers* hb, uint32_t phases) {
     CU(cudaEventRecord(s->ev_join[i], s->streams[i]));
     CU(cudaStreamWaitEvent(origin, s->ev_join[i], 0));
   }
+  if (phases & PPK_PHASE_STATS) {
+    // the logged sums (TILT:763-766, ADOF:1164-1168): fold the session's slots, hand the 8 doubles to the caller
+    int rc = ppk_stats_reduce(s->stats, s->stats_out, origin);
+    if (rc != PPK_OK) return rc;
+    CU(cudaMemcpyAsync(hb->stats, s->stats_out, sizeof(double) * PPK_NUM_STATS, cudaMemcpyDeviceToHost, origin));
+    s->d2h_bytes += sizeof(double) * PPK_NUM_STATS;
+  }
   if (adof_deferred) {
     // ADOF:1162-1175: any reset in the shard clears the five counters of ALL envs
     PpkBuffers db;
@@ -288,7 +316,7 @@ int ppk_host_session_destroy(PpkHostSession* s) {
   for (cudaStream_t st : s->streams)
     if (st) cudaStreamDestroy(st);
   void* ptrs[] = {s->rb, s->root, s->dof, s->force, s->pre, s->init_root, s->init_dof, s->init_rb, s->reset_vel,
-                  s->reset_yz, s->obs, s->rew, s->reset, s->progress, s->last_hitter, s->stats, s->scratch};
+                  s->reset_yz, s->obs, s->rew, s->reset, s->progress, s->last_hitter, s->stats, s->stats_out, s->scratch};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (uint8_t* f : s->flags)
@@ -333,7 +361,10 @@ int ppk_host_session_create(const PpkTask* task, int64_t max_envs, int32_t num_c
       d.paddle_body[h] = row < 0 ? 0 : row;
     }
   }
-  if (task->variant != PPK_BASE) ++next;   // pad row: keeps the bulk staging windows in bounds
+  if (task->variant != PPK_BASE) {
+    ++next;                    // pad row: keeps the ADOF bulk staging windows in bounds
+    if (next & 1) ++next;      // an even row count: env pairs are 16-byte multiples (tensor-map staging of the family kernel)
+  }
   s->dev_bodies = next;
   d.num_bodies = next;
   const int A = task->num_actors, D = task->num_dofs;
@@ -363,6 +394,7 @@ int ppk_host_session_create(const PpkTask* task, int64_t max_envs, int32_t num_c
   if (rc == PPK_OK && task->variant == PPK_ALIGN2) rc = dmalloc(&s->last_hitter, n);
   for (int i = 0; i < s->num_flags && rc == PPK_OK; ++i) rc = dmalloc(&s->flags[i], n);
   if (rc == PPK_OK) rc = dmalloc(&s->stats, (size_t)PPK_STATS_SLOTS * PPK_NUM_STATS);
+  if (rc == PPK_OK) rc = dmalloc(&s->stats_out, (size_t)PPK_NUM_STATS);
   if (rc == PPK_OK) rc = dmalloc(&s->scratch, 16);
   if (rc == PPK_OK && cudaMemset(s->stats, 0, sizeof(double) * PPK_STATS_SLOTS * PPK_NUM_STATS) != cudaSuccess) rc = PPK_ERR_CUDA;
   if (rc == PPK_OK && cudaMemset(s->scratch, 0, 64) != cudaSuccess) rc = PPK_ERR_CUDA;
@@ -402,12 +434,12 @@ int ppk_host_post_physics_step(PpkHostSession* s, const PpkBuffers* hb, uint32_t
       if (!hb->flags[i]) return PPK_ERR_NULL;
   if (v == PPK_ALIGN2 && (rew || rst) && !hb->last_hitter) return PPK_ERR_NULL;
   if (v == PPK_ADOF && (!hb->initial_body_states || !hb->initial_dof_states || (rst && !hb->reset_ball_pos_yz))) return PPK_ERR_NULL;
+  if ((phases & PPK_PHASE_STATS) && !hb->stats) return PPK_ERR_NULL;     // host [PPK_NUM_STATS] doubles receiving the sums
 
-  // constant tensors (initial states, launch table) go up when their host pointers change
-  const void* csrc[5] = {hb->initial_root_states, hb->initial_dof_states, hb->initial_body_states, hb->reset_ball_vel,
-                         hb->reset_ball_pos_yz};
+  // constant tensors (the initial states: TILT:186,214, ADOF:200) go up when their host pointers or the env count change
+  const void* csrc[3] = {hb->initial_root_states, hb->initial_dof_states, hb->initial_body_states};
   int64_t const_bytes = 0;
-  if (!s->constants_uploaded || memcmp(csrc, s->const_src, sizeof(csrc)) != 0) {
+  if (!s->constants_uploaded || s->const_n != n || memcmp(csrc, s->const_src, sizeof(csrc)) != 0) {
     cudaStream_t st = s->streams[0];
     if (hb->initial_root_states) { CU(cudaMemcpyAsync(s->init_root, hb->initial_root_states, sizeof(float) * n * A * kRow, cudaMemcpyHostToDevice, st)); const_bytes += sizeof(float) * n * A * kRow; }
     if (hb->initial_dof_states) { CU(cudaMemcpyAsync(s->init_dof, hb->initial_dof_states, sizeof(float) * n * D * 2, cudaMemcpyHostToDevice, st)); const_bytes += sizeof(float) * n * D * 2; }
@@ -418,14 +450,9 @@ int ppk_host_post_physics_step(PpkHostSession* s, const PpkBuffers* hb, uint32_t
                              sizeof(float) * r.rows * kRow, n, cudaMemcpyHostToDevice, st));
         const_bytes += sizeof(float) * r.rows * kRow * n;
       }
-    if (hb->reset_ball_vel) {
-      size_t cnt = (v == PPK_BASE) ? 6 : (size_t)n * 3;
-      CU(cudaMemcpyAsync(s->reset_vel, hb->reset_ball_vel, sizeof(float) * cnt, cudaMemcpyHostToDevice, st));
-      const_bytes += sizeof(float) * cnt;
-    }
-    if (hb->reset_ball_pos_yz) { CU(cudaMemcpyAsync(s->reset_yz, hb->reset_ball_pos_yz, sizeof(float) * n * 2, cudaMemcpyHostToDevice, st)); const_bytes += sizeof(float) * n * 2; }
     CU(cudaStreamSynchronize(st));
     memcpy(s->const_src, csrc, sizeof(csrc));
+    s->const_n = n;
     s->constants_uploaded = true;
   }
 
@@ -441,6 +468,7 @@ int ppk_host_post_physics_step(PpkHostSession* s, const PpkBuffers* hb, uint32_t
     for (int i = 0; i < s->num_flags; ++i) zc = zc && is_pinned_host(hb->flags[i]);
     zc = zc && is_pinned_host(hb->last_hitter);
     s->zero_copy = zc;
+    s->zc_launch = is_pinned_host(hb->reset_ball_vel) && is_pinned_host(hb->reset_ball_pos_yz) && hb->reset_ball_vel != nullptr;
     s->key = *hb;
     s->key_phases = phases;
     s->key_valid = true;

@@ -42,32 +42,38 @@ base_step_kernel(const __grid_constant__ KArgs k) {
   // reset_idx of the envs flagged by the PREVIOUS step's reward (BASE:589-591)
   const bool base_resets = (phases & PPK_PHASE_RESET) && on && k.reset[env] != 0;
   if (phases & PPK_PHASE_RESET) append_reset_indices(k, base_resets, env, lane);
-  if (k.timeout != nullptr && on) k.timeout[env] = (prog >= k.max_len - 1) ? 1 : 0;
   // the warp resets its flagged envs one after the other, all lanes copying (coalesced rows instead of one
   // lane walking 35 + 2*52 floats)
   for (unsigned pending = __ballot_sync(0xffffffffu, base_resets); pending != 0; pending &= pending - 1) {
     const long long e = env0 + (__ffs(pending) - 1);
     const float* ir = k.init_root + (size_t)e * rootN;
-    float* ge = k.root + (size_t)e * rootN;
+    float* go = k.root_out + (size_t)e * rootN;             // = the input rows unless the caller splits the reset output off
     for (int f = lane; f < k.A * 7; f += 32) {              // pos + rot; velocities are NOT zeroed (BASE:533-534)
       const int a = f / 7, c = f - a * 7;
-      ge[a * kRow + c] = ir[a * kRow + c];
+      go[a * kRow + c] = ir[a * kRow + c];
     }
     if (lane < 6)                                           // ball1 <- velocity_1, ball2 <- velocity_2 (BASE:549-550)
-      ge[(k.ball + lane / 3) * kRow + 7 + lane % 3] = k.reset_vel[lane];
-    const float* id = k.init_dof + (size_t)e * 2 * k.D;
-    float* gd = k.dof + (size_t)e * 2 * k.D;
-    for (int i = lane; i < 2 * k.D; i += 32) gd[i] = id[i];
+      go[(k.ball + lane / 3) * kRow + 7 + lane % 3] = k.reset_vel[lane];
+    if (k.reset_dof) {                                      // BASE:552 (PpkTask.reset_dof; initial_dof_states required with it)
+      const float* id = k.init_dof + (size_t)e * 2 * k.D;
+      float* gd = k.dof_out + (size_t)e * 2 * k.D;
+      for (int i = lane; i < 2 * k.D; i += 32) gd[i] = id[i];
+    }
   }
   __syncwarp();                                             // the observations below read the rows just written
   if (base_resets) prog = 0;
+  // time-out as BASE's reward sees it: from the progress AFTER the reset cleared it (BASE:587-596, 665)
+  if (k.timeout != nullptr && on) k.timeout[env] = (prog >= k.max_len - 1) ? 1 : 0;
   if (on && (phases & (PPK_PHASE_PROGRESS | PPK_PHASE_RESET))) k.progress[env] = prog;
 
   if (base_resets) {
+    // velocities 10:13 of the ball rows are not part of the obs, 7:10 were just rewritten: read the rows back
+    const float* r1 = k.root_out + (size_t)env * rootN + k.ball * kRow;
+    const float* r2 = r1 + kRow;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      o[12 + c] = b1[c]; o[15 + c] = b1[7 + c];
-      o[18 + c] = b2[c]; o[21 + c] = b2[7 + c];
+      o[12 + c] = r1[c]; o[15 + c] = r1[7 + c];
+      o[18 + c] = r2[c]; o[21 + c] = r2[7 + c];
     }
   }
   if (phases & PPK_PHASE_OBS) {

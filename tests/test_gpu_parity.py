@@ -531,11 +531,13 @@ def test_baseline_sizes_match_oracle(variant, n, with_pre):
 
 def test_adof_has_fallen_at_the_threshold():
     """ADOF's `has_fallen` compares a MEAN of 23 fp32 norms with 0.32 (ADOF:1412): the only flag of the path that
-    hangs on a reduction.  Every env here is planted so that the mean lands within a few ulp of 0.32.  Where the
-    fp64 value of the same fp32 inputs is more than 2 ulp(0.32) away from the threshold every fp32 summation order
-    gives the same answer: the kernel (shuffle tree) must agree with the oracle (ATen's CPU order) exactly.  Inside
-    +-2 ulp the reference's own answer depends on the reduction order of the ATen build it runs on (CPU vector ISA,
-    or the CUDA reduce kernel in production), so either answer is the reference's: those envs are only counted."""
+    hangs on a reduction.  Every env here is planted so that the mean lands within +-32 ulp of 0.32.  A sum of 23
+    norms of ~0.32 passes through partial sums of up to 7.4 (ulp 4.8e-7): each of the 22 additions may err by half
+    of that, 0.35 ulp(0.32) once divided by 23, so two fp32 summation orders can disagree by up to ~8 ulp(0.32).
+    Where the fp64 value of the same fp32 inputs is more than 8 ulp away from the threshold every order gives the
+    same answer: the kernel (shuffle tree) must agree with the oracle (ATen's CPU order) exactly.  Inside +-8 ulp
+    the reference's own answer depends on the reduction order of the ATen build it runs on (CPU vector ISA, or
+    the CUDA reduce kernel in production), so either answer is the reference's: those envs are only counted."""
     cfg = CONFIGS["adof"]
     n = 8192
     st = make_state(cfg, n, seed=4321, adversarial=False)
@@ -544,24 +546,25 @@ def test_adof_has_fallen_at_the_threshold():
     ref = st["initial_body_states"][:, bal, 0:3].double()
     d = torch.randn(n, len(bal), 3, generator=gen, dtype=torch.float64)
     ulp = 2.0 ** -25                                          # ulp of fp32 in [0.25, 0.5)
-    aim = 0.32 + (torch.rand(n, generator=gen, dtype=torch.float64) * 32.0 - 16.0) * ulp     # +-16 ulp around 0.32
+    aim = 0.32 + (torch.rand(n, generator=gen, dtype=torch.float64) * 64.0 - 32.0) * ulp     # +-32 ulp around 0.32
     d = d * (aim / d.norm(dim=-1).mean(dim=-1))[:, None, None]
     st["rigid_body_states"][:, bal, 0:3] = (ref + d).float()
     for name in cfg.counter_names:
         st[name][:] = False
+    st["progress_buf"][:] = 0          # no time-outs: a reset anywhere would clear the counters of the shard (ADOF:1171-1175)
     cur = st["rigid_body_states"][:, bal, 0:3]
     exact = (cur.double() - st["initial_body_states"][:, bal, 0:3].double()).norm(dim=-1).mean(dim=-1)
     margin = (exact - float(torch.tensor(0.32, dtype=torch.float32))) / ulp
-    assert int((margin.abs() < 2).sum()) > n // 40 and int((margin.abs() > 2).sum()) > n // 2, "the planted batch does not straddle the threshold"
+    assert int((margin.abs() < 8).sum()) > n // 8 and int((margin.abs() > 8).sum()) > n // 2, "the planted batch does not straddle the threshold"
     want, _ = oracle_full_step(cfg, st)
     g = gpu_state(st)
     run(cfg, g, N.PHASE_ALL)
     got_fall, want_fall = g["fall_down_count"].cpu(), want["fall_down_count"]
-    clear = margin.abs() > 2.0
+    clear = margin.abs() > 8.0
     assert torch.equal(got_fall[clear], want_fall[clear]), "has_fallen differs where no fp32 summation order can flip it"
     assert torch.equal(want_fall[clear], (margin > 0)[clear])
     flips = int((got_fall != want_fall)[~clear].sum())
-    print(f"has_fallen: {int((~clear).sum())} envs within 2 ulp of 0.32, {flips} of them decided differently by the two summation orders")
+    print(f"has_fallen: {int((~clear).sum())} envs within 8 ulp of 0.32, {flips} of them decided differently by the two summation orders")
     # everything else of those envs is still compared, with the envs whose flag legitimately differs left out
     same = got_fall == want_fall
     for name in STATE_EXACT + cfg.flag_names:
