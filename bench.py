@@ -14,7 +14,13 @@ statistics all-reduce.
 
 Timing hygiene: >= 3 warm-up steps; the step rotates over `--sets` (default 8) independent state
 sets (~190 MB each for TILT, far beyond the 126 MB L2) so inputs are never L2-resident; timed on
-the device with CUDA events around exactly K steps replayed from CUDA graphs; max over ranks.
+the device with CUDA events around exactly K steps replayed from CUDA graphs (every graph is replayed
+once, untimed, before the events: the first replay of a freshly instantiated graph is slower); max
+over ranks.  Every `log_every` steps (TILT:763, A3:741, ADOF:860) the step accumulates the logged
+sums and -- inside the timed region, on a side stream -- they are folded and all-reduced over the ranks
+(8 doubles, NCCL): the only collective of the path, shown to stay off the step's critical path.
+At N > 1 rank 0's line also carries BASELINE.json configs[3] (A4 and ADOF, 262144 envs sharded over the
+ranks) and configs[4] (ALIGN pre + post step, 131072 envs per GPU), timed on all ranks at once.
 """
 import argparse
 import ctypes as C
@@ -49,8 +55,17 @@ ALGO_BYTES = {"base": 212 + 8, "a3": 708 + 8, "tilt": 718 + 8, "nes": 716 + 8, "
               "adof": 3198 + 8}
 PRE_STEP_BYTES = {"align": 72}
 OTHER_STEPS = 2048          # timed steps of each context workload (other_workloads)
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the ncu --set full captures under profiles/
-NCU_TRAFFIC = {("tilt", 65536): 68.15e6 + 3.0e6, ("adof", 32768): 113.55e6 + 15.8e6, ("a4", 65536): 116.09e6 + 16.6e6}
+
+
+def ncu_traffic(variant, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel, parsed by profiles/summarize.py
+    from the committed `ncu --set full` captures into profiles/ncu_traffic.json (None when no capture matches)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = d.get(f"{variant}@{n}")
+        return None if e is None else float(e["dram_read_bytes"]) + float(e["dram_write_bytes"])
+    except Exception:
+        return None
 
 
 def measured_hbm_peak():
@@ -183,43 +198,84 @@ def make_tasks(variant, n, sets, device, seed_base):
 
 def time_steps(tasks, steps, warmup, with_pre, log_every, world, dist):
     """Exactly `steps` task steps replayed from CUDA graphs, CUDA-event timed; returns seconds
-    (max over ranks) and the number of kernels launched in the timed region."""
+    (max over ranks) and the number of our kernels launched in the timed region.
+
+    The step sequence is cut at the logging steps (i % log_every == 0): [logging step] [the plain steps up to the
+    next one].  After each logging step the side stream folds the statistics slots (`ppk_stats_reduce`) and
+    all-reduces the 8 doubles over the ranks while the main stream carries on with the plain steps."""
     from isaacgym_b200 import _native as N
     sets = len(tasks)
-    counter = {"i": 0}
+    dev = tasks[0].device
+    lib = tasks[0]._lib
+    adof = tasks[0].cfg.variant == "adof"
 
-    def one_step():
-        i = counter["i"]
+    def one_step(i, log):
         t = tasks[i % sets]
         if with_pre:
             N.check(t._lib.ppk_pre_physics_step(t._task, t.buffers(), t._stream()), "pre")
-        phases = N.PHASE_ALL if (log_every > 0 and i % log_every == 0) else (N.PHASE_ALL & ~N.PHASE_STATS)
-        t._step(phases)
-        counter["i"] = i + 1
+        t._step(N.PHASE_ALL if log else (N.PHASE_ALL & ~N.PHASE_STATS))
 
-    for _ in range(max(warmup, 3)):          # eager warm-up (also sets the kernels' smem attributes)
-        one_step()
+    for i in range(max(warmup, 3)):          # eager warm-up (also sets the kernels' smem attributes)
+        one_step(i, False)
     torch.cuda.synchronize()
-    chunk = min(steps, 512)
-    full, rem = divmod(steps, chunk)
-    graphs = []
-    for count in ([chunk] if full else []) + ([rem] if rem else []):
+
+    # segments: (first step index, count, first step logs); graphs are shared by segments that look the same
+    segs, i = [], 0
+    while i < steps:
+        log = log_every > 0 and i % log_every == 0
+        if log:
+            segs.append((i, 1, True))
+            i += 1
+            continue
+        nxt = steps if log_every <= 0 else min(steps, (i // log_every + 1) * log_every)
+        cnt = min(nxt - i, 512)
+        segs.append((i, cnt, False))
+        i += cnt
+    graphs = {}
+    for first, cnt, log in segs:
+        key = (first % sets, cnt, log)
+        if key in graphs:
+            continue
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for _ in range(count):
-                one_step()
-        graphs.append((g, count))
+            for j in range(cnt):
+                one_step(first + j, log)
+        graphs[key] = g
+    torch.cuda.synchronize()
+    for g in graphs.values():                # untimed first replay of every graph
+        g.replay()
+    # every set shares ONE slots tensor per task; the logging steps of set s accumulate into tasks[s].stats.slots
+    side = torch.cuda.Stream(dev)
+    main = torch.cuda.current_stream(dev)
+    local = torch.zeros(N.PPK_NUM_STATS, dtype=torch.float64, device=dev)
+    total = torch.zeros(N.PPK_NUM_STATS, dtype=torch.float64, device=dev)
+    for t in tasks:
+        t.stats.slots.zero_()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_log, ev_side = torch.cuda.Event(), torch.cuda.Event()
+    reduces = 0
     start.record()
-    if full:
-        for _ in range(full):
-            graphs[0][0].replay()
-    if rem:
-        graphs[-1][0].replay()
+    for first, cnt, log in segs:
+        if log and reduces:
+            main.wait_event(ev_side)         # the previous fold has left the slots (never a real wait)
+        graphs[(first % sets, cnt, log)].replay()
+        if log:
+            ev_log.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev_log)
+                slots = tasks[first % sets].stats.slots
+                N.check(lib.ppk_stats_reduce(slots.data_ptr(), local.data_ptr(), side.cuda_stream), "ppk_stats_reduce")
+                total.copy_(local, non_blocking=True)
+                if world > 1:
+                    dist.all_reduce(total, op=dist.ReduceOp.SUM)      # 8 doubles over NVLink, off the critical path
+                ev_side.record(side)
+            reduces += 1
+    if reduces:
+        main.wait_event(ev_side)             # the last collective ends inside the timed region
     end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -230,8 +286,8 @@ def time_steps(tasks, steps, warmup, with_pre, log_every, world, dist):
         t = torch.tensor([sec], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
-    per_step = 1 + (1 if with_pre else 0) + (1 if tasks[0].cfg.variant == "adof" else 0)   # ADOF: + counter-clear kernel
-    return sec, steps * per_step
+    per_step = 1 + (1 if with_pre else 0) + (1 if adof else 0)   # ADOF: + counter-clear kernel
+    return sec, steps * per_step + reduces, total.cpu().tolist()
 
 
 def run_e2e(variant, n, steps, device, chunks=4):
@@ -281,6 +337,29 @@ def run_cpu(variant, n, steps, warmup, threads):
     return times
 
 
+def config_dict(workload_desc, variant, n, world, sets, with_pre):
+    """`config` of the JSON line -- the same dict for our arm and the reference arm (same workload, same N)."""
+    return {"workload": workload_desc, "variant": variant, "envs_per_gpu": n, "global_envs": n * world,
+            "parallelism": f"env-sharded x{world}, stats all-reduce only",
+            "l2_defeat": f"rotating {sets} independent state sets per GPU (inputs larger than L2)",
+            "pre_physics_step_in_step": with_pre, "launch": "CUDA graph replay"}
+
+
+def bench_workload(name, n, sets, steps, warmup, device, rank, world, dist, peak):
+    """One context workload (BASELINE.json configs other than the headline one), all ranks at once."""
+    from isaacgym_b200.config import CONFIGS
+    v, _, desc, pre = WORKLOADS[name]
+    cfg, tasks = make_tasks(v, n, sets, device, seed_base=99 + 17 * rank)
+    sec, _, _ = time_steps(tasks, steps, warmup, pre, cfg.log_every, world, dist)
+    algo = ALGO_BYTES[v] + (PRE_STEP_BYTES.get(v, 0) if pre else 0)
+    ach = algo * n / (sec / steps) / 1e9
+    del tasks
+    torch.cuda.empty_cache()
+    return {"workload": desc, "envs_per_gpu": n, "global_envs": n * world, "value": n * world * steps / sec,
+            "unit": "env-steps/s", "ms_per_step": 1e3 * sec / steps, "roofline_frac": ach / peak, "achieved_gbs": ach,
+            "state_sets": sets, "steps": steps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -300,6 +379,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
+    warm = max(args.warmup, 3)
 
     if args.impl == "reference":
         # the reference's own CPU path: its ATen op chains (oracle port; /root/reference cannot travel
@@ -307,16 +387,16 @@ def main():
         if rank != 0:
             return
         steps = max(1, min(args.steps, 20))
-        warm = max(1, min(args.warmup, 3))
-        times = run_cpu(variant, n, steps, warm, cores)
+        times = run_cpu(variant, n, steps, min(warm, 3), cores)
         sec = sum(times)
         value = n * len(times) / sec
         line = {"impl": "reference", "metric": "env-steps/sec of fused obs+reward+reset", "value": value,
                 "unit": "env-steps/s", "n_gpus": args.gpus, "steps": len(times), "warmup": warm,
                 "ms_per_step": 1e3 * sec / len(times), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_desc, "variant": variant, "envs_per_gpu": n,
-                           "note": "CPU run of the reference's ATen op sequence (oracle port), one process"},
+                "config": config_dict(workload_desc, variant, n, args.gpus, args.sets, with_pre),
+                "reference_note": "CPU run of the reference's ATen op sequence (oracle port), one process on rank 0's host "
+                                  f"cores; at most 20 timed steps of the full {n}-env batch",
                 "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                  "sample": f"{len(times)} steps of the full {n}-env batch"},
                 "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -337,15 +417,9 @@ def main():
     cfg, tasks = make_tasks(variant, n, args.sets, device, seed_base=1000 * CONFIGS[variant].variant_id + 17 * rank)
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
-    sec, launches = time_steps(tasks, args.steps, args.warmup, with_pre, cfg.log_every, world, dist)
+    sec, launches, totals = time_steps(tasks, args.steps, args.warmup, with_pre, cfg.log_every, world, dist)
     clocks = sampler.stop()
-    # the only collective of the path: 8 doubles, off the critical path.  One logging step outside
-    # the timed region gives a clean sample (the slots also hold the logging steps of the timed loop).
-    tasks[0].stats.slots.zero_()
-    tasks[0]._step(N.PHASE_ALL)
-    tasks[0].stats.reduce(tasks[0]._lib, tasks[0]._stream())
-    stat_means = tasks[0].stats.means(n * world)
-    torch.cuda.synchronize()
+    stat_means = {name: x / (n * world) for name, x in zip(N.STAT_NAMES, totals)}   # the last logging step's all-reduced sums
 
     total_envs = n * world
     value = total_envs * args.steps / sec
@@ -353,24 +427,23 @@ def main():
     peak, peak_src = measured_hbm_peak()
     algo = ALGO_BYTES[variant] + (PRE_STEP_BYTES.get(variant, 0) if with_pre else 0)
     achieved = algo * n / (sec / args.steps) / 1e9          # per GPU: every rank runs the same shard size
+    traffic = ncu_traffic(variant, n)
     line = {
         "metric": "env-steps/sec of fused obs+reward+reset", "value": value, "unit": "env-steps/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_desc, "variant": variant, "envs_per_gpu": n, "global_envs": total_envs,
-                   "parallelism": f"env-sharded x{world}, stats all-reduce only",
-                   "l2_defeat": f"rotating {args.sets} independent state sets per GPU (inputs larger than L2)",
-                   "pre_physics_step_in_step": with_pre, "launch": "CUDA graph replay"},
+        "config": config_dict(workload_desc, variant, n, world, args.sets, with_pre),
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC.get((variant, n)), "algorithmic_bytes_per_env": algo, "peak_source": peak_src,
+                     "traffic": traffic, "algorithmic_bytes_per_env": algo, "peak_source": peak_src,
                      "kernel": f"family_step_kernel<{variant}>" if variant not in ("base", "adof") else f"{variant}_step_kernel",
                      "note": "achieved = algorithmic bytes per launch / (CUDA-event time of the timed region / launches). "
                              "traffic = dram__bytes_read + dram__bytes_write of one launch from the committed ncu capture "
-                             "(profiles/): reads are ~1.9x the algorithmic read bytes because the AoS rows are 52 B and "
-                             "DRAM moves 64-B granules; most of the 343 B/env of outputs are still in L2 when the launch "
-                             "ends and reach DRAM later, so the step's real traffic is ~1.36 kB/env vs 726 B algorithmic"},
+                             "(profiles/ncu_traffic.json): the AoS rows are 52 B, the TMA engine fetches 64-B granules, and most "
+                             "of the 343 B/env of outputs are still in L2 when the launch ends and reach DRAM later"},
+        "stats_collective": {"every_steps": cfg.log_every, "in_timed_region": True, "stream": "side",
+                             "payload": "8 doubles, all-reduce(SUM)" if world > 1 else "8 doubles (single rank: fold only)"},
         "stats_sample": {k: stat_means[k] for k in ("reward_sum", "progress_sum", "reset_count")},
     }
     if rank == 0 and not args.no_extras and variant != "base":
@@ -382,16 +455,35 @@ def main():
     del tasks
     torch.cuda.empty_cache()
 
-    if rank == 0 and not args.no_extras:
-        # e2e through the host-buffer C-ABI session, this rank's shard (N=1: the whole job)
+    if not args.no_extras:
+        # e2e through the host-buffer C-ABI session: EVERY rank runs its own shard at the same time (they share the
+        # host's memory and PCIe complex), the job's throughput is all envs over the slowest rank's wall time
         try:
+            if world > 1:
+                dist.barrier()
             e_sec, h2d, d2h = run_e2e(variant, n, args.e2e_steps, device)
-            line["e2e"] = {"value": n * args.e2e_steps / e_sec * world, "unit": "env-steps/s",
-                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+            if world > 1:
+                t = torch.tensor([e_sec], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e_sec = float(t.item())
+            line["e2e"] = {"value": n * world * args.e2e_steps / e_sec, "unit": "env-steps/s",
+                           "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": args.e2e_steps,
                            "note": "ppk_host_post_physics_step: pinned host state tensors, chunked H2D/kernel/D2H "
-                                   "pipeline; measured on rank 0's shard and scaled by the rank count"}
+                                   "pipeline; measured on all ranks at once, max wall time over the ranks"}
         except Exception as e:  # noqa: BLE001
             line["e2e"] = {"value": None, "unit": "env-steps/s", "error": str(e)[:200]}
+    if not args.no_extras and world > 1:
+        # BASELINE.json configs[3] (A4 and ADOF, 262144 envs sharded over the ranks: strong scaling) and configs[4]
+        # (ALIGN pre + post step at 131072 envs per GPU), all ranks at once, the stats all-reduce in the loop
+        others = {}
+        for name, n2, sets2 in (("a4", 262144 // world, 4), ("adof", 262144 // world, 4), ("align", 131072, 4)):
+            try:
+                r = bench_workload(name, n2, sets2, 1024, 16, device, rank, world, dist, peak)
+                r["scaling"] = "strong (262144 envs over the ranks)" if name != "align" else "weak (131072 envs per GPU)"
+                others[name] = r
+            except Exception as e:  # noqa: BLE001
+                others[name] = {"error": str(e)[:200]}
+        line["other_workloads"] = others
     if rank == 0 and world == 1 and not args.no_extras:
         # CPU baseline: the oracle port on the host cores, bounded sample of the same workload
         times = run_cpu(variant, n, 10, 2, cores)
@@ -406,17 +498,8 @@ def main():
             if name == args.workload:
                 continue
             try:
-                v2, n2, desc2, pre2 = WORKLOADS[name]
-                sets2 = 8 if n2 <= 131072 else 2
-                cfg2, tasks2 = make_tasks(v2, n2, sets2, device, seed_base=99)
-                s2, _ = time_steps(tasks2, OTHER_STEPS, 16, pre2, 0, 1, None)
-                algo2 = ALGO_BYTES[v2] + (PRE_STEP_BYTES.get(v2, 0) if pre2 else 0)
-                ach2 = algo2 * n2 / (s2 / OTHER_STEPS) / 1e9
-                others[name] = {"workload": desc2, "envs": n2, "value": n2 * OTHER_STEPS / s2, "unit": "env-steps/s",
-                                "ms_per_step": 1e3 * s2 / OTHER_STEPS, "roofline_frac": ach2 / peak, "achieved_gbs": ach2,
-                                "state_sets": sets2}
-                del tasks2
-                torch.cuda.empty_cache()
+                n2 = WORKLOADS[name][1]
+                others[name] = bench_workload(name, n2, 8 if n2 <= 131072 else 2, OTHER_STEPS, 16, device, 0, 1, None, peak)
             except Exception as e:  # noqa: BLE001
                 others[name] = {"error": str(e)[:200]}
         line["other_workloads"] = others

@@ -76,13 +76,13 @@ constexpr uint32_t kPhaseDeferCounterClear = 1u << 8;   // internal (host sessio
 #ifndef PPK_ADOF_MINB
 #define PPK_ADOF_MINB 8        // CTAs per SM with the compact reference pose (27 KB smem, 48 registers)
 #endif
-template <bool COMPACT>
+template <bool COMPACT, bool CLIP = false>
 __global__ void __launch_bounds__(kAdofThreads, COMPACT ? PPK_ADOF_MINB : 6)
 adof_step_kernel(const __grid_constant__ KArgs k) {
   using L = AdofLayout<COMPACT>;
   extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float clip = k.clip_obs;
+  const float clip = CLIP ? k.clip_obs : 0.0f;      // VecTask.step's observation clamp: its own instantiation, free when off
   const long long env0 = (long long)blockIdx.x * kAdofTile;
   const int nvalid = (int)min((long long)kAdofTile, k.n - env0);
   constexpr int D = kAdofD, J = kAdofJ, NB = kAdofNB, T = kAdofTile;
@@ -466,9 +466,11 @@ inline int launch_adof(const KArgs& k0, cudaStream_t s) {
   for (const void* p : al) bulk = bulk && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
   k.bulk_ok = bulk ? 1 : 0;
   const size_t smem = (size_t)(compact ? AdofLayout<true>::kFloats : AdofLayout<false>::kFloats) * sizeof(float);
-  static SmemOptIn opt_full, opt_compact;
-  if (!opt_full.ensure(adof_step_kernel<false>, AdofLayout<false>::kFloats * sizeof(float)) ||
-      !opt_compact.ensure(adof_step_kernel<true>, AdofLayout<true>::kFloats * sizeof(float)))
+  static SmemOptIn opt_full, opt_compact, opt_full_c, opt_compact_c;
+  if (!opt_full.ensure(adof_step_kernel<false, false>, AdofLayout<false>::kFloats * sizeof(float)) ||
+      !opt_compact.ensure(adof_step_kernel<true, false>, AdofLayout<true>::kFloats * sizeof(float)) ||
+      !opt_full_c.ensure(adof_step_kernel<false, true>, AdofLayout<false>::kFloats * sizeof(float)) ||
+      !opt_compact_c.ensure(adof_step_kernel<true, true>, AdofLayout<true>::kFloats * sizeof(float)))
     return PPK_ERR_LAUNCH;
   const bool fused_reset = (k.phases & PPK_PHASE_RESET) != 0 && !(k.phases & kPhaseDeferCounterClear);
   const long long tiles = (k.n + kAdofTile - 1) / kAdofTile;
@@ -478,8 +480,8 @@ inline int launch_adof(const KArgs& k0, cudaStream_t s) {
     if (occ == 0) {
       int dev = 0, o = 0, n_sm = 0;
       const bool ok = cudaGetDevice(&dev) == cudaSuccess &&
-                      (compact ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, adof_step_kernel<true>, kAdofThreads, smem)
-                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, adof_step_kernel<false>, kAdofThreads, smem)) == cudaSuccess &&
+                      (compact ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, adof_step_kernel<true, false>, kAdofThreads, smem)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, adof_step_kernel<false, false>, kAdofThreads, smem)) == cudaSuccess &&
                       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && o > 0 && n_sm > 0;
       if (ok) { occ = o; sms = n_sm; } else cudaGetLastError();
     }
@@ -493,8 +495,11 @@ inline int launch_adof(const KArgs& k0, cudaStream_t s) {
     k.first_wave = occ * sms;
     k.stagger = (occ > 0 && tiles > (long long)occ * sms) ? stag : 0;
   }
-  if (compact) adof_step_kernel<true><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
-  else adof_step_kernel<false><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
+  const bool clip = k.clip_obs > 0.0f;
+  if (compact && !clip) adof_step_kernel<true, false><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
+  else if (compact) adof_step_kernel<true, true><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
+  else if (!clip) adof_step_kernel<false, false><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
+  else adof_step_kernel<false, true><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
   if (cudaGetLastError() != cudaSuccess) return PPK_ERR_LAUNCH;
   if (fused_reset) return launch_adof_clear(k.scratch, k.flags, k.n, s);
   return PPK_OK;

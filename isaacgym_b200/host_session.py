@@ -30,6 +30,9 @@ class HostSession:
                 v = v.cpu()
             self.state[k] = v.pin_memory() if (pin and v.numel() > 0 and torch.cuda.is_available()) else v
         self.num_envs = self.state["progress_buf"].shape[0]
+        # with PPK_PHASE_STATS the session folds its device slots and returns the sums of the call here (PpkStat order)
+        stats = torch.zeros(N.PPK_NUM_STATS, dtype=torch.float64)
+        self.state["stats"] = stats.pin_memory() if (pin and torch.cuda.is_available()) else stats
         self._buf = N.make_buffers(cfg, self.state, host=True)
         self._sess = C.c_void_p()
         N.check(self._lib.ppk_host_session_create(N.make_task(cfg), self.num_envs, num_chunks, C.byref(self._sess)),
@@ -37,6 +40,10 @@ class HostSession:
 
     def post_physics_step(self, phases: int = N.PHASE_ALL & ~N.PHASE_STATS):
         N.check(self._lib.ppk_host_post_physics_step(self._sess, self._buf, phases), "ppk_host_post_physics_step")
+
+    def stats_means(self):
+        """Per-env means of the sums returned by the last call that included PHASE_STATS."""
+        return {name: float(x) / self.num_envs for name, x in zip(N.STAT_NAMES, self.state["stats"].tolist())}
 
     def traffic(self):
         h2d, d2h = C.c_int64(), C.c_int64()

@@ -40,7 +40,14 @@ class PingpongTask(VecTask):
 
     def __init__(self, sim_state: Dict[str, torch.Tensor], cfg: Optional[TaskConfig] = None,
                  device: str = "cuda:0", fused: bool = True, full_pre_ball_clone: bool = False,
-                 log_stats: bool = False, envelope: bool = False, compact_reference_pose: bool = True, **kw):
+                 log_stats: bool = False, envelope: bool = False, compact_reference_pose: bool = True,
+                 launch_seed: Optional[int] = 0, env_offset: int = 0, **kw):
+        """`launch_seed`: the reference draws a fresh ball launch velocity inside every reset (TILT:857-862).  Here the
+        fused reset consumes row n of the per-env launch table `reset_ball_vel`; after every `post_physics_step` the rows
+        just consumed are redrawn on the device (`ppk_sample_ball_launch`, Philox keyed by (launch_seed, env, step)), so
+        no env ever replays a launch.  `launch_seed=None` leaves the table alone: it is then an explicit input the
+        caller refills (parity tests feed the oracle the same table).  `env_offset`: first global env id of this shard
+        (data-parallel ranks draw disjoint counter ranges)."""
         cfg = cfg or CONFIGS[self.variant]
         n = sim_state["root_states"].shape[0]
         super().__init__(cfg, n, device=device, **kw)
@@ -49,6 +56,8 @@ class PingpongTask(VecTask):
         self._lib = N.load()
         self._task = N.make_task(cfg)
         self.fused = fused
+        self.launch_seed = launch_seed
+        self.env_offset = env_offset
         self.log_stats = log_stats
         self.envelope = envelope          # also emit timeout_buf + compacted reset index lists (VecTask.step envelope)
         self._count_zeroed = False
@@ -212,6 +221,10 @@ class PingpongTask(VecTask):
             self.compute_observations()
         if log:
             self.stats.reduce(self._lib, self._stream())
+        if self.launch_seed is not None and self.cfg.variant != "base":
+            # redraw the launch rows of the envs that just reset (reset_buf still holds this step's mask, TILT:900)
+            self.sample_ball_launch(self.launch_seed, epoch=self.num_steps + 1, env_offset=self.env_offset,
+                                    refresh_consumed_only=True)
         self.num_steps += 1
 
 

@@ -26,7 +26,8 @@ def test_bench_line_has_the_contract_keys():
         assert key in d, key
     assert d["steps"] == 40 and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["vs_baseline"] is None
     assert d["dtype"] == "f32" and d["data"] == "synthetic" and "workload" in d["config"]
-    assert d["gpu_launches"] == 40 and d["value"] > 0
+    assert d["gpu_launches"] == 40 + 1 and d["value"] > 0      # 40 step kernels + the fold of the one logging step (i = 0)
+    assert d["stats_collective"]["in_timed_region"] is True
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     e = d["e2e"]
@@ -42,3 +43,5 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"]
+    ours = _run("--steps", "8", "--warmup", "3", "--envs-per-gpu", "4096", "--sets", "2", "--no-extras")
+    assert ours["config"] == d["config"] and ours["metric"] == d["metric"] and ours["unit"] == d["unit"]   # same_config for the driver

@@ -146,7 +146,7 @@ def test_multi_step_trajectory(variant):
     n = 512
     st = make_state(cfg, n, seed=21)
     o = clone_state(st)
-    task = make_task(variant, st, device=DEV, full_pre_ball_clone=(variant == "align"))
+    task = make_task(variant, st, device=DEV, full_pre_ball_clone=(variant == "align"), launch_seed=None)
     gen = torch.Generator().manual_seed(5)
     b = cfg.ball_actor
     for step in range(12):
@@ -621,3 +621,44 @@ def test_golden_step_fixture(variant):
     got = g["reset_actor_indices"][:k * cfg.num_actors].cpu().view(k, cfg.num_actors)
     want = outs["reset_actor_indices"].view(-1, cfg.num_actors)
     assert k == want.shape[0] and torch.equal(got[got[:, 0].argsort()], want[want[:, 0].argsort()])
+
+
+@pytest.mark.parametrize("variant", ["tilt", "adof", "base"])
+@pytest.mark.parametrize("pin", [True, False])
+def test_host_session_launch_table_is_a_per_step_input(variant, pin):
+    """The launch table is refilled IN PLACE between steps (same host pointers, graph replay from the third call on):
+    every reset must consume the fresh values, as the reference draws a new velocity per reset (TILT:857-862).  The
+    session also returns the logged sums of a PHASE_STATS call (PpkStat order) in its host `stats` array."""
+    from isaacgym_b200.host_session import HostSession
+    cfg = CONFIGS[variant]
+    n = 2048
+    st = make_state(cfg, n, seed=61)
+    if variant == "base":
+        st["reset_buf"] = (torch.rand(n, generator=torch.Generator().manual_seed(3)) < 0.1).to(torch.int64)
+        st["reset_ball_vel"] = st["reset_ball_vel"][:2].contiguous()
+    dev = gpu_state(st)
+    if variant != "base":
+        dev["pre_ball_states"] = dev["pre_ball_states"][:, [7, 9]].contiguous()
+    sess = HostSession(cfg, st, num_chunks=2, pin=pin)
+    gen = torch.Generator().manual_seed(8)
+    try:
+        for step in range(5):
+            vel = torch.randn(sess.state["reset_ball_vel"].shape, generator=gen)
+            sess.state["reset_ball_vel"].copy_(vel)               # in place: the pointer the session saw before
+            dev["reset_ball_vel"].copy_(vel.to(DEV))
+            if variant == "adof":
+                yz = torch.randn(n, 2, generator=gen)
+                sess.state["reset_ball_pos_yz"].copy_(yz)
+                dev["reset_ball_pos_yz"].copy_(yz.to(DEV))
+            dev["stats"].zero_()
+            sess.post_physics_step(N.PHASE_ALL)
+            run(cfg, dev, N.PHASE_ALL)
+            for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "root_states", "dof_states") + cfg.flag_names + cfg.counter_names:
+                assert torch.equal(sess.state[name], dev[name].cpu()), f"{variant} step {step}: {name}"
+            want = dev["stats"].sum(dim=0).cpu()
+            got = sess.state["stats"]
+            assert float(got[1]) == float(want[1]) and float(got[2]) == float(want[2])
+            assert abs(float(got[0]) - float(want[0])) <= 1e-9 * max(1.0, abs(float(want[0])))
+        assert int(dev["reset_buf"].sum()) > 0
+    finally:
+        sess.close()
