@@ -197,17 +197,23 @@ def make_tasks(variant, n, sets, device, seed_base):
 
 
 def time_steps(tasks, steps, warmup, with_pre, log_every, world, dist):
-    """Exactly `steps` task steps replayed from CUDA graphs, CUDA-event timed; returns seconds
-    (max over ranks) and the number of our kernels launched in the timed region.
+    """Exactly `steps` task steps replayed from CUDA graphs, CUDA-event timed; returns seconds (max over ranks), the
+    number of our kernels launched in the timed region and the last all-reduced statistics vector.
 
-    The step sequence is cut at the logging steps (i % log_every == 0): [logging step] [the plain steps up to the
-    next one].  After each logging step the side stream folds the statistics slots (`ppk_stats_reduce`) and
-    all-reduces the 8 doubles over the ranks while the main stream carries on with the plain steps."""
+    Logging steps (i % log_every == 0, as the reference logs: TILT:763, A3:741, ADOF:860) accumulate the statistics;
+    right after each of them the graph FORKS: a side branch folds the slots (`ppk_stats_reduce`) and all-reduces the 8
+    doubles over the ranks (NCCL, captured into the graph) while the main branch carries on with the next steps; the
+    branches join before the next logging step / at the end of the graph.  The collective is inside the timed region
+    and off the step's critical path.  If this torch / NCCL build cannot capture the collective, it is issued eagerly
+    on the side stream after each graph instead (same work, one exposed latency at the end of the region)."""
     from isaacgym_b200 import _native as N
     sets = len(tasks)
     dev = tasks[0].device
     lib = tasks[0]._lib
     adof = tasks[0].cfg.variant == "adof"
+    side = torch.cuda.Stream(dev)
+    local = torch.zeros(N.PPK_NUM_STATS, dtype=torch.float64, device=dev)
+    total = torch.zeros(N.PPK_NUM_STATS, dtype=torch.float64, device=dev)
 
     def one_step(i, log):
         t = tasks[i % sets]
@@ -215,67 +221,89 @@ def time_steps(tasks, steps, warmup, with_pre, log_every, world, dist):
             N.check(t._lib.ppk_pre_physics_step(t._task, t.buffers(), t._stream()), "pre")
         t._step(N.PHASE_ALL if log else (N.PHASE_ALL & ~N.PHASE_STATS))
 
+    def fold(i, collective):
+        """on the current (side) stream: slots of the logging step's task -> local -> total (-> all-reduce)"""
+        slots = tasks[i % sets].stats.slots
+        N.check(lib.ppk_stats_reduce(slots.data_ptr(), local.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "ppk_stats_reduce")
+        total.copy_(local, non_blocking=True)
+        if collective and world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.SUM)      # 8 doubles over NVLink
+
     for i in range(max(warmup, 3)):          # eager warm-up (also sets the kernels' smem attributes)
         one_step(i, False)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)          # the communicator exists before anything is captured
     torch.cuda.synchronize()
 
-    # segments: (first step index, count, first step logs); graphs are shared by segments that look the same
+    def is_log(i):
+        return log_every > 0 and i % log_every == 0
+
+    def capture(first, cnt, collective):
+        g = torch.cuda.CUDAGraph()
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.graph(g):
+            cap = torch.cuda.current_stream(dev)
+            forked = False
+            for j in range(cnt):
+                i = first + j
+                if is_log(i):
+                    if forked:
+                        cap.wait_stream(side)                 # the previous fold has left the slots
+                    one_step(i, True)
+                    side.wait_stream(cap)                     # fork
+                    with torch.cuda.stream(side):
+                        fold(i, collective)
+                    forked = True
+                else:
+                    one_step(i, False)
+            if forked:
+                cap.wait_stream(side)                         # join
+        del main
+        return g
+
+    # segments of <= 512 steps; segments that look the same (start set, length, phase of the logging cadence) share a graph
     segs, i = [], 0
     while i < steps:
-        log = log_every > 0 and i % log_every == 0
-        if log:
-            segs.append((i, 1, True))
-            i += 1
-            continue
-        nxt = steps if log_every <= 0 else min(steps, (i // log_every + 1) * log_every)
-        cnt = min(nxt - i, 512)
-        segs.append((i, cnt, False))
+        cnt = min(steps - i, 512)
+        segs.append((i, cnt))
         i += cnt
+    period = log_every if log_every > 0 else 1
+    in_graph_collective = True
     graphs = {}
-    for first, cnt, log in segs:
-        key = (first % sets, cnt, log)
+    for first, cnt in segs:
+        key = (first % sets, cnt, first % period)
         if key in graphs:
             continue
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for j in range(cnt):
-                one_step(first + j, log)
-        graphs[key] = g
+        if in_graph_collective:
+            try:
+                graphs[key] = capture(first, cnt, True)
+            except Exception:  # noqa: BLE001 -- this build cannot capture the collective: fold in the graph, all-reduce eagerly
+                torch.cuda.synchronize()
+                in_graph_collective = False
+        if not in_graph_collective:
+            graphs[key] = capture(first, cnt, False)
     torch.cuda.synchronize()
     for g in graphs.values():                # untimed first replay of every graph
         g.replay()
-    # every set shares ONE slots tensor per task; the logging steps of set s accumulate into tasks[s].stats.slots
-    side = torch.cuda.Stream(dev)
-    main = torch.cuda.current_stream(dev)
-    local = torch.zeros(N.PPK_NUM_STATS, dtype=torch.float64, device=dev)
-    total = torch.zeros(N.PPK_NUM_STATS, dtype=torch.float64, device=dev)
     for t in tasks:
         t.stats.slots.zero_()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    main = torch.cuda.current_stream(dev)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev_log, ev_side = torch.cuda.Event(), torch.cuda.Event()
-    reduces = 0
+    folds = sum(1 for i in range(steps) if is_log(i))
+    eager = world > 1 and not in_graph_collective and folds > 0
     start.record()
-    for first, cnt, log in segs:
-        if log and reduces:
-            main.wait_event(ev_side)         # the previous fold has left the slots (never a real wait)
-        graphs[(first % sets, cnt, log)].replay()
-        if log:
-            ev_log.record(main)
+    for first, cnt in segs:
+        graphs[(first % sets, cnt, first % period)].replay()
+        if eager and any(is_log(i) for i in range(first, first + cnt)):
+            side.wait_stream(main)
             with torch.cuda.stream(side):
-                side.wait_event(ev_log)
-                slots = tasks[first % sets].stats.slots
-                N.check(lib.ppk_stats_reduce(slots.data_ptr(), local.data_ptr(), side.cuda_stream), "ppk_stats_reduce")
-                total.copy_(local, non_blocking=True)
-                if world > 1:
-                    dist.all_reduce(total, op=dist.ReduceOp.SUM)      # 8 doubles over NVLink, off the critical path
-                ev_side.record(side)
-            reduces += 1
-    if reduces:
-        main.wait_event(ev_side)             # the last collective ends inside the timed region
+                dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    if eager:
+        main.wait_stream(side)               # the last collective ends inside the timed region
     end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -287,7 +315,11 @@ def time_steps(tasks, steps, warmup, with_pre, log_every, world, dist):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
     per_step = 1 + (1 if with_pre else 0) + (1 if adof else 0)   # ADOF: + counter-clear kernel
-    return sec, steps * per_step + reduces, total.cpu().tolist()
+    time_steps.collective_mode = ("captured in the step graph" if in_graph_collective else "eager on the side stream") if world > 1 else "single rank: fold only"
+    return sec, steps * per_step + folds, total.cpu().tolist()
+
+
+time_steps.collective_mode = ""
 
 
 def run_e2e(variant, n, steps, device, chunks=4):
@@ -442,8 +474,8 @@ def main():
                              "traffic = dram__bytes_read + dram__bytes_write of one launch from the committed ncu capture "
                              "(profiles/ncu_traffic.json): the AoS rows are 52 B, the TMA engine fetches 64-B granules, and most "
                              "of the 343 B/env of outputs are still in L2 when the launch ends and reach DRAM later"},
-        "stats_collective": {"every_steps": cfg.log_every, "in_timed_region": True, "stream": "side",
-                             "payload": "8 doubles, all-reduce(SUM)" if world > 1 else "8 doubles (single rank: fold only)"},
+        "stats_collective": {"every_steps": cfg.log_every, "in_timed_region": True, "stream": "side branch of the step graph",
+                             "payload": "8 doubles, all-reduce(SUM)", "mode": time_steps.collective_mode},
         "stats_sample": {k: stat_means[k] for k in ("reward_sum", "progress_sum", "reset_count")},
     }
     if rank == 0 and not args.no_extras and variant != "base":

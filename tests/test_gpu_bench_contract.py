@@ -39,7 +39,7 @@ def test_bench_line_has_the_contract_keys():
 
 
 def test_reference_arm_line():
-    d = _run("--impl", "reference", "--steps", "2", "--warmup", "1", "--envs-per-gpu", "4096")
+    d = _run("--impl", "reference", "--steps", "2", "--warmup", "1", "--envs-per-gpu", "4096", "--sets", "2")
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"]
