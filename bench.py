@@ -175,6 +175,50 @@ def run_learner_side(tasks, units, peak, iters=40, warm=5):
         nbytes = rows * width * 4 + (rows * units * 2 if name == "first_layer" else 0)
         res[name] = {"us": sec * 1e6, "rows_per_s": rows / sec, "achieved_gbs": nbytes / sec / 1e9,
                      "roofline_frac": nbytes / sec / 1e9 / peak}
+    # the same update fed by the step kernel itself (PPK_PHASE_MOMENTS): step + fold vs step, then + separate update
+    from isaacgym_b200 import _native as N
+    if tasks[0].cfg.variant not in ("base", "adof"):
+        for t in tasks:
+            t.fused_moments = True
+            t.obs_moments = torch.zeros(N.PPK_MOMENT_SLOTS, 2 * width, dtype=torch.float64, device=dev)
+            t._buffers = None
+        rms2 = RunningMeanStd(width, device=dev)
+        ph = N.PHASE_ALL & ~N.PHASE_STATS
+
+        def timed(fn):
+            for i in range(warm):
+                fn(tasks[i % len(tasks)])
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(iters):
+                    fn(tasks[i % len(tasks)])
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e3 / iters
+
+        def plain(t):
+            t._step(ph)
+
+        def with_update(t):
+            t._step(ph)
+            rms2.update(t.obs_buf.view(-1, width))
+
+        def fused(t):
+            t._step(ph | N.PHASE_MOMENTS)
+            rms2.update_from_step(t.obs_moments, rows)
+
+        res["step_plus_rms_update"] = {"step_us": timed(plain), "step_then_update_us": timed(with_update),
+                                       "step_with_fused_moments_us": timed(fused),
+                                       "note": "CUDA-graph replay of (task step [+ RunningMeanStd update]) over the rotating state sets"}
+        for t in tasks:
+            t.fused_moments = False
+            t._buffers = None
     res["first_layer"].update({"units": units, "dtype": "f16 operands, f32 accumulate (tcgen05), f16 out",
                                "tflops": 2.0 * rows * width * units / (res["first_layer"]["us"] * 1e-6) / 1e12,
                                "bound": "hbm (the [rows, units] fp16 write)"})

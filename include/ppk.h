@@ -38,6 +38,7 @@ extern "C" {
 #define PPK_MAX_FLAGS 12      /* bool flag / counter tensors of one variant            */
 #define PPK_STATS_SLOTS 64    /* stats[PPK_STATS_SLOTS][PPK_NUM_STATS] partial sums     */
 #define PPK_NUM_STATS 8
+#define PPK_MOMENT_SLOTS 64   /* obs_moments[PPK_MOMENT_SLOTS][2 * num_obs] partial column sums  */
 
 typedef enum PpkError {
   PPK_OK = 0,
@@ -69,7 +70,12 @@ typedef enum PpkPhase {
   PPK_PHASE_RESET = 4,     /* reset_idx(nonzero(reset_buf)), per env     TILT:1034-1036   */
   PPK_PHASE_OBS = 8,       /* compute_observations: obs_buf              TILT:770-799     */
   PPK_PHASE_STATS = 16,    /* accumulate the logged statistics           TILT:763-766     */
-  PPK_PHASE_ALL = 31
+  PPK_PHASE_ALL = 31,
+  /* not part of the task step proper (opt-in, needs PPK_PHASE_OBS): while the obs tile of
+   * a CTA is still in shared memory, add its fp64 column sums and sums of squares to PpkBuffers.obs_moments, so that
+   * the learner's RunningMeanStd update (normalize_input: True) never re-reads obs_buf: ppk_rms_fold_step_moments.
+   * A3 / TILT / NES / ALIGN / A4 / ALIGN2. */
+  PPK_PHASE_MOMENTS = 32
 } PpkPhase;
 
 /* Statistics accumulated per slot (sum over envs; divide by N on the host). */
@@ -196,6 +202,9 @@ typedef struct PpkBuffers {
    * produce it (upstream VecTask.step: obs = clamp(obs_buf, -clip_obs, clip_obs); the upstream default
    * is inf = no clamp, and no YAML of the reference sets clipObservations).  <= 0: off. */
   float clip_observations;
+  /* PPK_PHASE_MOMENTS: PPK_MOMENT_SLOTS x (2 * num_obs) doubles, zero-initialised by the caller once; slot s holds
+   * [sum_r obs[r, :], sum_r obs[r, :]^2] of the CTAs that hash to it (rows = envs, or (env, humanoid) pairs for A4). */
+  double* obs_moments;
 } PpkBuffers;
 
 PPK_API int ppk_abi_version(void);
@@ -287,6 +296,11 @@ PPK_API int ppk_rms_accumulate(const PpkRunningMeanStd* rms, const float* obs, i
 /* RunningMeanStd._update_mean_var_count_from_moments with the batch mean / unbiased variance of the
  * `batch_rows` rows accumulated in `moments`; clears `moments`. */
 PPK_API int ppk_rms_merge(const PpkRunningMeanStd* rms, double batch_rows, void* stream);
+/* The moments a step kernel accumulated with PPK_PHASE_MOMENTS: rms->moments[0..2W) += sum over the slots of
+ * `obs_moments` (which are cleared), then -- merge != 0 -- ppk_rms_merge with `batch_rows` (merge == 0: data-parallel
+ * ranks all-reduce rms->moments and the row count first, then call ppk_rms_merge). */
+PPK_API int ppk_rms_fold_step_moments(const PpkRunningMeanStd* rms, double* obs_moments, double batch_rows, int32_t merge,
+                                      void* stream);
 /* RunningMeanStd.forward in training mode, single rank: accumulate + merge. */
 PPK_API int ppk_rms_update(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, void* stream);
 /* RunningMeanStd.forward output: out = clamp((clamp(obs) - float(mean)) / sqrt(float(var) + eps), -5, 5), fp32. */

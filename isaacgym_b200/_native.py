@@ -15,6 +15,8 @@ ABI_VERSION = 2
 
 PHASE_PROGRESS, PHASE_REWARD, PHASE_RESET, PHASE_OBS, PHASE_STATS = 1, 2, 4, 8, 16
 PHASE_ALL = 31
+PHASE_MOMENTS = 32          # opt-in: column moments of obs_buf for RunningMeanStd (learner side)
+PPK_MOMENT_SLOTS = 64
 
 STAT_NAMES = ("reward_sum", "progress_sum", "reset_count", "fall_down_count", "closer_to_paddle_count",
               "hit_paddle_count", "cross_net_count", "hit_table_count")
@@ -53,7 +55,7 @@ class PpkBuffers(C.Structure):
         ("actor_indices", C.c_void_p), ("dof_indices", C.c_void_p), ("reset_count", C.c_void_p),
         ("reset_actor_indices", C.c_void_p), ("reset_dof_indices", C.c_void_p),
         ("last_hitter", C.c_void_p), ("initial_balance_states", C.c_void_p),
-        ("clip_observations", C.c_float),
+        ("clip_observations", C.c_float), ("obs_moments", C.c_void_p),
     ]
 
 
@@ -124,6 +126,8 @@ def load():
     lib.ppk_rms_accumulate.argtypes = [rp, C.c_void_p, C.c_int64, C.c_void_p]
     lib.ppk_rms_merge.restype = C.c_int
     lib.ppk_rms_merge.argtypes = [rp, C.c_double, C.c_void_p]
+    lib.ppk_rms_fold_step_moments.restype = C.c_int
+    lib.ppk_rms_fold_step_moments.argtypes = [rp, C.c_void_p, C.c_double, C.c_int32, C.c_void_p]
     lib.ppk_rms_update.restype = C.c_int
     lib.ppk_rms_update.argtypes = [rp, C.c_void_p, C.c_int64, C.c_void_p]
     lib.ppk_rms_normalize.restype = C.c_int
@@ -241,6 +245,7 @@ def make_buffers(cfg: TaskConfig, st: dict, host: bool = False) -> PpkBuffers:
     b.stats = _ptr(st.get("stats"), torch.float64, "stats", host)
     b.scratch = _ptr(st.get("scratch"), torch.int32, "scratch", host)
     b.last_hitter = _ptr(st.get("last_hitter"), i64, "last_hitter", host)
+    b.obs_moments = _ptr(st.get("obs_moments"), torch.float64, "obs_moments", host)
     # optional VecTask.step envelope outputs
     b.clip_actions = float(st.get("clip_actions", 0.0) or 0.0)
     clip_obs = float(st.get("clip_observations", 0.0) or 0.0)

@@ -180,20 +180,27 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
       hd[H_A0] = 2.0f * (hq.cw * hq.cw) - 1.0f; hd[H_SZ] = hq.sz; hd[H_CW] = hq.cw;
     }
     asm volatile("bar.sync 3, %0;" ::"n"(32 * kAdofObsWarps) : "memory");
-#pragma unroll 1
-    for (int e = warp - 1; e < T; e += kAdofObsWarps) {
+    // Pass 1, both envs of this warp: imitation diffs and the per-env reductions warp 0's reward waits for; then the
+    // warp ARRIVES, and only then (pass 2) spends its time on the observation segments -- the reward phase of warp 0
+    // overlaps the obs stores instead of queueing behind them.
+    constexpr int EPW = T / kAdofObsWarps;        // envs per obs warp
+    static_assert(T % kAdofObsWarps == 0, "every obs warp owns the same number of envs");
+    const bool body_on = lane < NB;
+    float dpx[EPW], dpy[EPW], dpz[EPW], dvx[EPW], dvy[EPW], dvz[EPW];
+#pragma unroll
+    for (int qi = 0; qi < EPW; ++qi) {
+      const int e = (warp - 1) + qi * kAdofObsWarps;
       const float* rb_e = rb_s + e * L::kSRb + win_off(g_rb, e);
       const float* in_e = init_s + e * L::kSInit + win_off(g_init, e);
       const float* cur = rb_e + bal_id * kRow;
-      const bool body_on = lane < NB;
       const float* ref = COMPACT ? in_e + (body_on ? lane : 0) * 6 : in_e + bal_id * kRow;
       const float* refv = ref + (COMPACT ? 3 : 7);
       // imitation diffs: ref - cur (ADOF:1345,1349 / ADOF:1908-1909)
-      float dpx = ref[0] - cur[0], dpy = ref[1] - cur[1], dpz = ref[2] - cur[2];
-      float dvx = refv[0] - cur[7], dvy = refv[1] - cur[8], dvz = refv[2] - cur[9];
+      dpx[qi] = ref[0] - cur[0]; dpy[qi] = ref[1] - cur[1]; dpz[qi] = ref[2] - cur[2];
+      dvx[qi] = refv[0] - cur[7]; dvy[qi] = refv[1] - cur[8]; dvz[qi] = refv[2] - cur[9];
       // per-body sums of squares; the /3 of the inner mean is applied once per env in phase R
-      float s_dp2 = body_on ? (dpx * dpx + dpy * dpy + dpz * dpz) : 0.0f;
-      float s_dv2 = body_on ? (dvx * dvx + dvy * dvy + dvz * dvz) : 0.0f;
+      float s_dp2 = body_on ? (dpx[qi] * dpx[qi] + dpy[qi] * dpy[qi] + dpz[qi] * dpz[qi]) : 0.0f;
+      float s_dv2 = body_on ? (dvx[qi] * dvx[qi] + dvy[qi] * dvy[qi] + dvz[qi] * dvz[qi]) : 0.0f;
       // has_fallen uses the norm of cur - ref (ADOF:1412): cur - ref == -(ref - cur) exactly and squares drop
       // the sign, so it is the square root of the same sum, bit for bit
       float s_nrm = sqrtf(s_dp2);
@@ -209,17 +216,28 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
       float s_pow = dof_on ? fabsf(force_s[e * D + dl] * qd) : 0.0f;
       // all seven sums in one butterfly: lane L ends up with the total of value (L >> 2) & 7
       const float red = warp_sum8(s_dp2, s_dv2, s_nrm, s_dq22, s_dq5, s_dqd22, s_pow, 0.0f, lane);
-      // heading frames: ping-pong root body and balance root body (both row 0 in the shipped config)
       const float* r0 = rb_e + pp_root * kRow;
       float* hd = hdr_s + e * L::kSHdr;
+      if ((lane & 3) == 0 && lane < 28) hd[H_SUM_DP2 + (lane >> 2)] = red;     // slots are consecutive
+      if (lane == 31) { hd[H_RX] = r0[0]; hd[H_RY] = r0[1]; hd[H_RZ] = r0[2]; }
+    }
+    adof_arrive();
+    if (!(phases & PPK_PHASE_OBS)) return;
+    // Pass 2: observation segments of the same envs
+#pragma unroll
+    for (int qi = 0; qi < EPW; ++qi) {
+      const int e = (warp - 1) + qi * kAdofObsWarps;
+      if (e >= nvalid) continue;
+      const float* rb_e = rb_s + e * L::kSRb + win_off(g_rb, e);
+      const float* r0 = rb_e + pp_root * kRow;
+      const float* hd = hdr_s + e * L::kSHdr;
+      // heading frames: ping-pong root body and balance root body (both row 0 in the shipped config)
       Heading hq_pp;
       hq_pp.sz = hd[H_SZ];
       hq_pp.cw = hd[H_CW];
       const float* b0 = rb_e + bal_root * kRow;
       Heading hq_bal = (bal_root == pp_root) ? hq_pp : heading_quat_inv(b0[3], b0[4], b0[5], b0[6]);
-      if ((lane & 3) == 0 && lane < 28) hd[H_SUM_DP2 + (lane >> 2)] = red;     // slots are consecutive
-      if (lane == 31) { hd[H_RX] = r0[0]; hd[H_RY] = r0[1]; hd[H_RZ] = r0[2]; }
-      if ((phases & PPK_PHASE_OBS) && e < nvalid) {
+      {
         // ping-pong bodies [0,60), lane = output float o: body o/3, component o%3 (ADOF:1849-1888);
         //   out_c = v_c*a0 + ((s1*v_o)*m)*2 == my_quat_rotate((0,0,sz,cw), v) component by component
         if (lane < 3 * J) {
@@ -235,8 +253,8 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
         }
         // imitation observation segments [121,190) = 10*R(dP), [190,259) = R(dV)
         float lp[3], lv[3];
-        rotate_heading(hq_bal, dpx, dpy, dpz, lp[0], lp[1], lp[2]);
-        rotate_heading(hq_bal, dvx, dvy, dvz, lv[0], lv[1], lv[2]);
+        rotate_heading(hq_bal, dpx[qi], dpy[qi], dpz[qi], lp[0], lp[1], lp[2]);
+        rotate_heading(hq_bal, dvx[qi], dvy[qi], dvz[qi], lv[0], lv[1], lv[2]);
         lp[0] *= 10.0f; lp[1] *= 10.0f; lp[2] *= 10.0f;
         float* orow = g_obs + (size_t)e * kAdofObs + (6 * J + 2 * D + 7);
         // [body][xyz] -> 69 consecutive floats: through shared memory.  This env's reference rows have been
@@ -255,7 +273,6 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
         }
       }
     }
-    adof_arrive();
     return;
   }
 
@@ -446,7 +463,7 @@ adof_step_kernel(const __grid_constant__ KArgs k) {
 inline int launch_adof_clear(unsigned int* scratch, unsigned char* const* flags, long long n, cudaStream_t s) {
   long long cb = (n / 4 + 255) / 256;
   if (cb < 1) cb = 1;
-  if (cb > 148 * 8) cb = 148 * 8;
+  if (cb > sm_count() * 8) cb = sm_count() * 8;
   adof_clear_counters_kernel<<<(unsigned)cb, 256, 0, s>>>(scratch, flags[4], flags[5], flags[6], flags[7], flags[8], n);
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }

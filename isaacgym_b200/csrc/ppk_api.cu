@@ -98,6 +98,7 @@ int fill_args(const PpkTask* t, const PpkBuffers* b, uint32_t phases, KArgs* k) 
   k->term_dist = t->is_train ? 0.32f : 1e6f;           // ADOF:1404-1410, is_g1 branch
   k->phases = (int)phases; k->write_flags = t->write_flags; k->reset_dof = t->reset_dof;
   k->clip_obs = b->clip_observations;
+  k->moments = b->obs_moments;
   // Tensor-map staging (family kernel): the rigid-body tensor is read as [N/2 env pairs, 2*B*13 floats], legal when
   // the tensors start 16-byte aligned, an env pair is a multiple of 16 bytes (B even), ids[1..J) are consecutive rows
   // (one run per env).  The boxes over-read <= 12 bytes on either side of a run; what falls outside a pair's row of
@@ -264,8 +265,13 @@ int ppk_post_physics_step(const PpkTask* t, const PpkBuffers* b, uint32_t phases
   KArgs k;
   int rc = fill_args(t, b, phases, &k);
   if (rc != PPK_OK) return rc;
-  if ((phases & ~((uint32_t)PPK_PHASE_ALL | kPhaseDeferCounterClear)) != 0 || (phases & PPK_PHASE_ALL) == 0)
+  if ((phases & ~((uint32_t)PPK_PHASE_ALL | PPK_PHASE_MOMENTS | kPhaseDeferCounterClear)) != 0 || (phases & PPK_PHASE_ALL) == 0)
     return PPK_ERR_VARIANT;
+  if (phases & PPK_PHASE_MOMENTS) {
+    if (t->variant == PPK_BASE || t->variant == PPK_ADOF || !(phases & PPK_PHASE_OBS)) return PPK_ERR_VARIANT;
+    if (!b->obs_moments) return PPK_ERR_NULL;
+    if (reinterpret_cast<uintptr_t>(b->obs_moments) & 7u) return PPK_ERR_ALIGN;
+  }
   if (b->num_envs == 0) return PPK_OK;      // empty shard: nothing to dereference
   rc = check_step_pointers(t, b, phases);
   if (rc != PPK_OK) return rc;
@@ -364,7 +370,7 @@ int ppk_pre_physics_step(const PpkTask* t, const PpkBuffers* b, void* stream) {
   if (b->num_envs == 0) return PPK_OK;
   const long long total = b->num_envs * t->num_dofs;
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
   pre_step_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       b->actions, b->clip_actions, b->pd_action_offset, b->pd_action_scale, b->pd_targets, b->num_envs, t->num_dofs, b->root_states,
       t->num_actors * kRow, t->ball_actor, save_ball ? b->pre_ball_states : nullptr, b->pre_ball_stride,
@@ -426,7 +432,8 @@ int rms_launch_moments(const PpkRunningMeanStd* rms, const RmsArgs& a, const flo
   if (R < 1) R = 1;
   if (R < (vec ? 8 : 2)) R = (wx * (vec ? 8 : 2) <= 1024) ? (vec ? 8 : 2) : R;     // the fold needs 2*VEC row slots
   long long blocks = (rows + (long long)R * 4 - 1) / ((long long)R * 4);
-  if (blocks > kRmsMaxCtas) blocks = kRmsMaxCtas;   // one CTA per SM
+  if (blocks > sm_count()) blocks = sm_count();   // one CTA per SM
+  if (blocks > kRmsMaxCtas) blocks = kRmsMaxCtas;
   if (blocks < 1) blocks = 1;
   const size_t smem = sizeof(double) * 2 * (vec ? 4 : 1) * R * wx;
   if (vec) {
@@ -462,6 +469,16 @@ int ppk_rms_merge(const PpkRunningMeanStd* rms, double batch_rows, void* stream)
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 
+int ppk_rms_fold_step_moments(const PpkRunningMeanStd* rms, double* obs_moments, double batch_rows, int32_t merge, void* stream) {
+  RmsArgs a;
+  int rc = rms_args(rms, &a);
+  if (rc != PPK_OK) return rc;
+  if (!rms->moments || !obs_moments) return PPK_ERR_NULL;
+  if (merge && !(batch_rows > 0.0)) return PPK_ERR_SHAPE;
+  rms_fold_step_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(a, rms->moments, obs_moments, batch_rows, merge);
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+
 int ppk_rms_update(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, void* stream) {
   RmsArgs a;
   int rc = rms_args(rms, &a);
@@ -484,7 +501,7 @@ int ppk_rms_normalize(const PpkRunningMeanStd* rms, const float* obs, int64_t ro
   int R = 256 / wx;
   if (R < 1) R = 1;
   long long blocks = (rows + R - 1) / R;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (vec) rms_apply_kernel<4><<<(unsigned)blocks, dim3(wx, R), 0, s>>>(a, obs, rows, out);
   else rms_apply_kernel<1><<<(unsigned)blocks, dim3(wx, R), 0, s>>>(a, obs, rows, out);
@@ -508,7 +525,7 @@ int ppk_linear_pack(const float* weight, const float* bias, int32_t units, int32
   if (need == 0 || packed_bytes < need) return PPK_ERR_SHAPE;
   if (reinterpret_cast<uintptr_t>(packed) & 15u) return PPK_ERR_ALIGN;
   const int kp = fl_kpad(width);
-  linear_pack_kernel<<<148 * 2, 256, 0, static_cast<cudaStream_t>(stream)>>>(weight, bias, units, width, kp,
+  linear_pack_kernel<<<sm_count() * 2, 256, 0, static_cast<cudaStream_t>(stream)>>>(weight, bias, units, width, kp,
                                                                               static_cast<__half*>(packed));
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
@@ -539,7 +556,7 @@ int launch_first_layer(const FlArgs& k, cudaStream_t s) {
   if (!opt0.ensure(first_layer_kernel<KP, KBLK, 0>, L::kBytes) || !opt1.ensure(first_layer_kernel<KP, KBLK, 1>, L::kBytes))
     return PPK_ERR_LAUNCH;
   const long long units = ((k.rows + kFlM - 1) / kFlM) * (k.units / kFlN);
-  const unsigned grid = (unsigned)(units < 148 ? units : 148);      // persistent: one CTA per SM
+  const unsigned grid = (unsigned)(units < sm_count() ? units : sm_count());      // persistent: one CTA per SM
   if (k.activation == PPK_ACT_ELU) first_layer_kernel<KP, KBLK, 1><<<grid, kFlThreads, L::kBytes, s>>>(k, out_map);
   else first_layer_kernel<KP, KBLK, 0><<<grid, kFlThreads, L::kBytes, s>>>(k, out_map);
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;

@@ -29,6 +29,19 @@ struct SmemOptIn {
   }
 };
 
+// SM count of the current device (grids are sized in multiples of it), queried once per device
+inline int sm_count() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return 148; }
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 constexpr int kRow = 13;  // floats per rigid-body / root-state row: pos3 quat4 linvel3 angvel3
 
 // Kernel arguments: the two C structs flattened, by value in param space.
@@ -79,6 +92,7 @@ struct KArgs {
   int* reset_count;
   int* reset_actor_out;
   int* reset_dof_out;
+  double* moments;           // PPK_PHASE_MOMENTS: [PPK_MOMENT_SLOTS][2 * obs width] fp64 column sums / sums of squares
   float clip_obs;            // > 0: observations are clamped to +-clip_obs where they are produced (VecTask.step)
   // tensor-map staging of the rigid-body rows (family kernel): inner coordinates (floats, 16-byte aligned) of the
   // boxes [humanoid][env parity] and where the wanted rows start inside them

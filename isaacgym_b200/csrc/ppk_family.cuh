@@ -501,19 +501,36 @@ family_step_kernel(const __grid_constant__ KArgs k, const __grid_constant__ CUte
 
   // ---- store the tile's obs rows ----------------------------------------------------------------------
   float* g_obs = k.obs + (size_t)env0 * H * L::kObs;
-  if (fast && (k.bulk_ok & 2)) {
+  const bool bulk_store = fast && (k.bulk_ok & 2);
+  if (bulk_store) {
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       bulk_s2g(g_obs, obs_s, 4u * L::kUnits * L::kObs);
       bulk_commit();
-      bulk_wait_read();
     }
   } else {
     __syncthreads();
     const int nfl = nvalid * H * L::kObs;
     for (int f = tid; f < nfl; f += kFamilyThreads) st_stream(g_obs + f, obs_s[f]);
   }
+  // ---- learner side, opt-in: column moments of the tile for RunningMeanStd, thread = column,
+  // while the rows are still on chip -- the normaliser's update never re-reads obs_buf
+  if ((phases & PPK_PHASE_MOMENTS) && tid < L::kObs) {
+    static_assert(L::kObs <= kFamilyThreads, "one thread per obs column");
+    double s = 0.0, ss = 0.0;
+    const int rows = nvalid * H;
+#pragma unroll 4
+    for (int u = 0; u < rows; ++u) {
+      const double v = (double)obs_s[u * L::kObs + tid];
+      s += v;
+      ss += v * v;
+    }
+    double* slot = k.moments + (size_t)(blockIdx.x % PPK_MOMENT_SLOTS) * 2 * L::kObs;
+    atomicAdd(slot + tid, s);
+    atomicAdd(slot + L::kObs + tid, ss);
+  }
+  if (bulk_store && tid == 0) bulk_wait_read();
 }
 
 }  // namespace ppk

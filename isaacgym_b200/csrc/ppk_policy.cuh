@@ -51,7 +51,7 @@ __device__ __forceinline__ void rms_merge_column(const RmsArgs& a, double* sums,
   sums[a.width + c] = 0.0;
 }
 
-constexpr int kRmsMaxCtas = 148;      // one CTA per SM
+constexpr int kRmsMaxCtas = 256;      // upper bound of the grid (one CTA per SM, sm_count() at launch)
 constexpr int kRmsSlots = 8;          // copies of the 2W accumulators the CTAs' atomics are spread over
 
 // Column sums and sums of squares of obs [rows, width] in fp64.  VEC = 4: threadIdx.x owns four adjacent
@@ -150,6 +150,39 @@ __global__ void rms_merge_kernel(RmsArgs a, double* sums, double batch_rows) {
   const double count = *a.count;
   __syncthreads();
   for (int c = threadIdx.x; c < a.width; c += blockDim.x) rms_merge_column(a, sums, batch_rows, count, c);
+  if (threadIdx.x == 0) *a.count = count + batch_rows;
+}
+
+// The column moments a step kernel left in PPK_MOMENT_SLOTS slot copies (PPK_PHASE_MOMENTS): fold them into sums[0..2W),
+// clear the slots, and (merge != 0) fold the batch into the running statistics.  One CTA: 2W <= 1024 sums of 64 doubles.
+__global__ void __launch_bounds__(1024)
+rms_fold_step_kernel(RmsArgs a, double* sums, double* slots, double batch_rows, int merge) {
+  // thread (g, c): column c of the 2W sums, slot copies g, g + G, ... (all loads of a thread in flight at once)
+  __shared__ double part[1024];
+  const int width = a.width, cols = 2 * width;
+  const int G = max(1, min((int)blockDim.x / cols, PPK_MOMENT_SLOTS));
+  const double count = *a.count;
+  const int per = blockDim.x / G;                 // columns handled per pass
+  for (int c0 = 0; c0 < cols; c0 += per) {
+    const int g = threadIdx.x / per, c = c0 + threadIdx.x % per;
+    double tot = 0.0;
+    if (g < G && c < cols) {
+#pragma unroll 4
+      for (int b = g; b < PPK_MOMENT_SLOTS; b += G) {
+        tot += __ldcg(slots + (size_t)b * cols + c);          // written by L2 atomics of the step kernel
+        slots[(size_t)b * cols + c] = 0.0;
+      }
+    }
+    part[threadIdx.x] = tot;
+    __syncthreads();
+    if (g == 0 && c < cols) {
+      for (int k = 1; k < G; ++k) tot += part[threadIdx.x + k * per];
+      sums[c] += tot;
+    }
+    __syncthreads();
+  }
+  if (!merge) return;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) rms_merge_column(a, sums, batch_rows, count, c);
   if (threadIdx.x == 0) *a.count = count + batch_rows;
 }
 

@@ -81,6 +81,29 @@ class RunningMeanStd:
             global_rows = rows.item()              # host read: pass global_rows to stay asynchronous
         N.check(self._lib.ppk_rms_merge(s, float(global_rows), N.current_stream_ptr()), "rms_merge")
 
+    def update_from_step(self, obs_moments: torch.Tensor, rows: int, group=None, global_rows: Optional[int] = None):
+        """The same merge from the column moments the fused task step left in `obs_moments`
+        ([PPK_MOMENT_SLOTS, 2*insize] float64, `PPK_PHASE_MOMENTS` / `PingpongTask(fused_moments=True)`) -- obs_buf is
+        not read again.  The moments are those of obs_buf as stored (clamp it in the step: `clip_observations`).
+        `rows`: rows of obs_buf the step wrote (envs, or 2 x envs for the two-humanoid variants)."""
+        if obs_moments.dtype != torch.float64 or not obs_moments.is_contiguous() or obs_moments.device != self.device \
+                or obs_moments.numel() != N.PPK_MOMENT_SLOTS * 2 * self.insize:
+            raise ValueError(f"expected a contiguous float64 [{N.PPK_MOMENT_SLOTS}, {2 * self.insize}] tensor on {self.device}")
+        s = self._struct()
+        if group is None:
+            N.check(self._lib.ppk_rms_fold_step_moments(s, obs_moments.data_ptr(), float(rows), 1, N.current_stream_ptr()),
+                    "rms_fold_step_moments")
+            return
+        import torch.distributed as dist
+        N.check(self._lib.ppk_rms_fold_step_moments(s, obs_moments.data_ptr(), float(rows), 0, N.current_stream_ptr()),
+                "rms_fold_step_moments")
+        dist.all_reduce(self._moments[:2 * self.insize], group=group)
+        if global_rows is None:
+            r = torch.tensor([float(rows)], dtype=torch.float64, device=self.device)
+            dist.all_reduce(r, group=group)
+            global_rows = r.item()
+        N.check(self._lib.ppk_rms_merge(s, float(global_rows), N.current_stream_ptr()), "rms_merge")
+
     def normalize(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         self._check(x)
         if out is None:

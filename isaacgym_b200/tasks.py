@@ -41,13 +41,15 @@ class PingpongTask(VecTask):
     def __init__(self, sim_state: Dict[str, torch.Tensor], cfg: Optional[TaskConfig] = None,
                  device: str = "cuda:0", fused: bool = True, full_pre_ball_clone: bool = False,
                  log_stats: bool = False, envelope: bool = False, compact_reference_pose: bool = True,
-                 launch_seed: Optional[int] = 0, env_offset: int = 0, **kw):
+                 launch_seed: Optional[int] = 0, env_offset: int = 0, fused_moments: bool = False, **kw):
         """`launch_seed`: the reference draws a fresh ball launch velocity inside every reset (TILT:857-862).  Here the
         fused reset consumes row n of the per-env launch table `reset_ball_vel`; after every `post_physics_step` the rows
         just consumed are redrawn on the device (`ppk_sample_ball_launch`, Philox keyed by (launch_seed, env, step)), so
         no env ever replays a launch.  `launch_seed=None` leaves the table alone: it is then an explicit input the
         caller refills (parity tests feed the oracle the same table).  `env_offset`: first global env id of this shard
-        (data-parallel ranks draw disjoint counter ranges)."""
+        (data-parallel ranks draw disjoint counter ranges).  `fused_moments`: the fused step also leaves the fp64
+        column moments of the obs rows it wrote in `self.obs_moments` (`PPK_PHASE_MOMENTS`), for
+        `RunningMeanStd.update_from_step` -- the normaliser's update then never re-reads obs_buf."""
         cfg = cfg or CONFIGS[self.variant]
         n = sim_state["root_states"].shape[0]
         super().__init__(cfg, n, device=device, **kw)
@@ -58,6 +60,9 @@ class PingpongTask(VecTask):
         self.fused = fused
         self.launch_seed = launch_seed
         self.env_offset = env_offset
+        self.fused_moments = bool(fused_moments) and cfg.variant not in ("base", "adof")
+        if self.fused_moments:
+            self.obs_moments = torch.zeros(N.PPK_MOMENT_SLOTS, 2 * cfg.num_obs, dtype=torch.float64, device=self.device)
         self.log_stats = log_stats
         self.envelope = envelope          # also emit timeout_buf + compacted reset index lists (VecTask.step envelope)
         self._count_zeroed = False
@@ -123,6 +128,8 @@ class PingpongTask(VecTask):
                  pre_ball_states=self.pre_ball2_root_states, actions=self.actions, pd_targets=self.pd_tar,
                  stats=self.stats.slots, scratch=self._scratch, clip_actions=self.clip_actions,
                  clip_observations=self.clip_obs)
+        if self.fused_moments:
+            d.update(obs_moments=self.obs_moments)
         if self.envelope:
             d.update(timeout_buf=self.timeout_buf)
         if self.envelope and "actor_indices" in self.st and "dof_indices" in self.st:
@@ -205,7 +212,7 @@ class PingpongTask(VecTask):
             self.reset_count.zero_()
         self._count_zeroed = False
         if self.fused:
-            self._step(N.PHASE_ALL if log else (N.PHASE_ALL & ~N.PHASE_STATS))
+            self._step((N.PHASE_ALL if log else (N.PHASE_ALL & ~N.PHASE_STATS)) | (N.PHASE_MOMENTS if self.fused_moments else 0))
         elif self.cfg.variant == "base":
             self._step(N.PHASE_PROGRESS | N.PHASE_RESET)
             self.compute_observations()

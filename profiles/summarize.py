@@ -2,7 +2,13 @@
 """Turn an `ncu --set full` report into the short text summary committed under profiles/.
 
     python profiles/summarize.py gpurun_out/prof.ncu-rep "title" > profiles/<name>.md
+    python profiles/summarize.py gpurun_out/prof.ncu-rep "title" --traffic tilt@65536 > profiles/<name>.md
+
+`--traffic <variant>@<envs>` also records the mean dram__bytes_read.sum / dram__bytes_write.sum per launch of the
+report in profiles/ncu_traffic.json, which is where bench.py reads `roofline.traffic` from.
 """
+import json
+import os
 import csv
 import io
 import subprocess
@@ -33,11 +39,32 @@ KEYS = [
 ]
 
 
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def record_traffic(rep, key, hdr, units, rows):
+    out = {}
+    for metric, name in (("dram__bytes_read.sum", "dram_read_bytes"), ("dram__bytes_write.sum", "dram_write_bytes"),
+                         ("gpu__time_duration.sum", "duration_ns")):
+        i = hdr.index(metric)
+        scale = UNIT.get(units[i], {"us": 1e3, "ns": 1.0, "ms": 1e6}.get(units[i], 1.0))
+        vals = [float(r[i].replace(",", "")) * scale for r in rows]
+        out[name] = sum(vals) / len(vals)
+    out["launches"] = len(rows)
+    out["source"] = rep
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_traffic.json")
+    d = json.load(open(path)) if os.path.exists(path) else {}
+    d[key] = out
+    json.dump(d, open(path, "w"), indent=1, sort_keys=True)
+
+
 def main():
     rep, title = sys.argv[1], sys.argv[2]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
+    if "--traffic" in sys.argv:
+        record_traffic(rep, sys.argv[sys.argv.index("--traffic") + 1], hdr, units, rows[2:])
     print(f"# {title}\n")
     print(f"source: `{rep}` (ncu --set full --clock-control none; per-launch values, cold-cache, serialised)\n")
     names = [r[hdr.index("Kernel Name")] for r in rows[2:]]

@@ -207,3 +207,31 @@ def test_first_layer_with_a_4_byte_aligned_observation_view():
     r2.running_mean.copy_(r1.running_mean); r2.running_var.copy_(r1.running_var)
     assert torch.equal(r1.normalize(x), r2.normalize(xa))
     assert torch.equal(FirstLayer(w, b, "elu", r1)(x), FirstLayer(w, b, "elu", r2)(xa))
+
+
+@pytest.mark.parametrize("variant,n", [("tilt", 4096), ("tilt", 1001), ("a4", 2000), ("nes", 65536)])
+def test_step_kernel_moments_feed_running_mean_std(variant, n):
+    """PPK_PHASE_MOMENTS: the fused task step leaves the fp64 column sums / sums of squares of the obs rows it wrote;
+    RunningMeanStd.update_from_step merges them without reading obs_buf -- same statistics as update(obs_buf) and as the
+    oracle's RunningMeanStd, over several steps (the slots are cleared by every fold)."""
+    from isaacgym_b200.config import CONFIGS
+    from isaacgym_b200.synth import make_state
+    from isaacgym_b200.tasks import make_task
+    cfg = CONFIGS[variant]
+    task = make_task(variant, make_state(cfg, n, seed=5), device=DEV, fused_moments=True, clip_observations=4.0)
+    fused, plain = RunningMeanStd(cfg.num_obs, device=DEV), RunningMeanStd(cfg.num_obs, device=DEV)
+    ref = P.RunningMeanStd(cfg.num_obs)
+    for step in range(3):
+        task.post_physics_step()
+        rows = task.obs_buf.view(-1, cfg.num_obs)
+        fused.update_from_step(task.obs_moments, rows.shape[0])
+        plain.update(rows)
+        ref.update(rows.cpu())
+        assert float(task.obs_moments.abs().sum()) == 0.0
+        for a, b in ((fused.running_mean, plain.running_mean), (fused.running_var, plain.running_var)):
+            torch.testing.assert_close(a, b, rtol=1e-11, atol=1e-12)
+        torch.testing.assert_close(fused.running_mean.cpu(), ref.running_mean, rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(fused.running_var.cpu(), ref.running_var, rtol=1e-6, atol=1e-7)
+        assert float(fused.count) == float(ref.count)
+        task.root_states[:, cfg.ball_actor, 0:3] += 0.01          # the next step sees other observations
+    assert float(task.obs_buf.abs().max()) <= 4.0
