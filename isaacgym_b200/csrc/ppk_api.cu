@@ -179,15 +179,17 @@ int check_step_pointers(const PpkTask* t, const PpkBuffers* b, uint32_t phases) 
   return PPK_OK;
 }
 
-// soft-start delay per first-wave slot, in SM cycles (profiles/r2_staging_probe.md); PPK_STAGGER overrides it
-int stagger_cycles() {
-  static int v = -1;
-  if (v < 0) {
+// Soft-start delay per first-wave slot, in SM cycles (profiles/r2_staging_probe.md): the time DRAM needs to serve one
+// tile's bytes to one SM (~1 cycle per 26 bytes of a CTA's shared memory: 1400 cycles for the 36 KB tiles; the 18 KB
+// tiles, twice as many slots per SM, measured best at 400); PPK_STAGGER overrides it (A/B runs)
+int stagger_cycles(size_t smem_bytes) {
+  static int forced = -2;
+  if (forced == -2) {
     const char* e = getenv("PPK_STAGGER");
-    v = e ? atoi(e) : 400;
-    if (v < 0) v = 0;
+    forced = e ? atoi(e) : -1;
   }
-  return v;
+  if (forced >= 0) return forced;
+  return smem_bytes > 24 * 1024 ? (int)(smem_bytes / 26) : (int)(smem_bytes / 46);
 }
 
 // the rigid-body tensor as [N/2 env pairs, 2*B*13 floats]; box = `box_floats` x `pairs` pairs
@@ -202,6 +204,19 @@ int make_rb_map(CUtensorMap* m, const float* rb, long long n, int num_bodies, in
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
              ? PPK_OK
              : PPK_ERR_CUDA;
+}
+
+// Up to ~2.5 waves of 32-env tiles (6 CTAs per SM) the step is latency- and tail-bound: 16-env tiles win (A3 16 384 envs
+// 7.3 -> 7.1 us, TILT 65 536 envs 15.55 -> 15.3 us); beyond, the full-lane 32-env tiles do (1 M envs: 186 vs 193 us).
+// PPK_SMALL_TILES=0/1 forces the choice (A/B runs, tests)
+bool small_batch(long long n) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("PPK_SMALL_TILES");
+    forced = e ? atoi(e) : -1;
+  }
+  if (forced >= 0) return forced != 0;
+  return (n + 31) / 32 <= 15LL * sm_count();
 }
 
 template <int V, int H, int J, int D, int A, int TILE>
@@ -236,7 +251,7 @@ int launch_family(const KArgs& k0, cudaStream_t s) {
   }
   k.num_sms = sms > 0 ? sms : 1;
   k.first_wave = occ * sms;
-  k.stagger = (occ > 0 && tiles > (long long)occ * sms) ? stagger_cycles() : 0;
+  k.stagger = (occ > 0 && tiles > (long long)occ * sms) ? stagger_cycles(smem) : 0;
   kern<<<(unsigned)tiles, kFamilyThreads, smem, s>>>(k, m_span, m_row0);
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
@@ -288,6 +303,14 @@ int ppk_post_physics_step(const PpkTask* t, const PpkBuffers* b, uint32_t phases
     case PPK_NES:
     case PPK_ALIGN:
       if (t->num_actors != 3 || t->num_dofs != 7 || t->num_body_ids != 10) return PPK_ERR_SHAPE;
+      // 32-env tiles use every lane of the lane = env warps; a batch that does not even fill one wave of them is
+      // latency-bound instead: 16-env tiles put twice as many CTAs to work and halve the rotation passes per CTA
+      if (small_batch(b->num_envs)) {
+        if (t->variant == PPK_A3) return launch_family<PPK_A3, 1, 10, 7, 3, 16>(k, s);
+        if (t->variant == PPK_TILT) return launch_family<PPK_TILT, 1, 10, 7, 3, 16>(k, s);
+        if (t->variant == PPK_NES) return launch_family<PPK_NES, 1, 10, 7, 3, 16>(k, s);
+        return launch_family<PPK_ALIGN, 1, 10, 7, 3, 16>(k, s);
+      }
       if (t->variant == PPK_A3) return launch_family<PPK_A3, 1, 10, 7, 3, 32>(k, s);
       if (t->variant == PPK_TILT) return launch_family<PPK_TILT, 1, 10, 7, 3, 32>(k, s);
       if (t->variant == PPK_NES) return launch_family<PPK_NES, 1, 10, 7, 3, 32>(k, s);

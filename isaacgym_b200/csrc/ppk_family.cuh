@@ -67,7 +67,7 @@ struct FamilyLayout {
   static constexpr int kOffBar = kOffObs + kUnits * kObs;              // two 8-byte mbarriers
   static constexpr int kFloats = kOffBar + 4;
   static constexpr uint32_t kLinearTx = 4u * TILE * (kRootEnv + 3 * D);
-  static_assert(kUnits == 32, "one heading per lane of warp 0");
+  static_assert(kUnits <= 32, "one heading per lane of warp 0");
   static_assert(TILE % 4 == 0 && TILE <= 32, "tile");
   static_assert((kPairs * kSpanF * 4) % 128 == 0 && (kPairs * 12 * 4) % 128 == 0, "128-byte tensor box destinations");
   static_assert((kOffRow0 * 4) % 128 == 0, "128-byte tensor box destinations");
@@ -227,7 +227,7 @@ family_step_kernel(const __grid_constant__ KArgs k, const __grid_constant__ CUte
     // ================= warp 0: heading frames (lane = unit), then rotations ==============================
     if (!want_obs) return;
     if (fast) mbar_wait(bar, 0);
-    {
+    if (lane < L::kUnits) {
       const int u = lane, e = u / H, h = u - e * H;
       const int so = span_at(e, h), ro = row0_at(e, h);
       const float* r0 = smem + ro;

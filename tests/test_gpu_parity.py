@@ -662,3 +662,21 @@ def test_host_session_launch_table_is_a_per_step_input(variant, pin):
         assert int(dev["reset_buf"].sum()) > 0
     finally:
         sess.close()
+
+
+def test_small_batches_also_pass_on_the_32_env_tiles():
+    """Batches below one wave of 32-env tiles run on 16-env tiles (ppk_api.cu small_batch), so most tests of this
+    file exercise those; PPK_SMALL_TILES=0 (read once per process) forces the 32-env instantiations onto the same
+    small / ragged cases, tail tiles included."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("PPK_SMALL_TILES") is not None:
+        pytest.skip("already inside the forced run")
+    env = dict(os.environ, PPK_SMALL_TILES="0")
+    here = os.path.abspath(__file__)
+    out = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-k",
+                          "(test_fused_step_matches_oracle or test_ragged_sizes or test_multi_step_trajectory or "
+                          "test_golden_step_fixture) and (tilt or a3 or nes or align)"],
+                         env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(here)))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
