@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "--shared", "-cudart", "shared",
-] + os.environ.get("PPK_NVCC_EXTRA", "").split()      # e.g. -DPPK_HALF_ANGLE_HEADING for A/B builds
+] + os.environ.get("PPK_NVCC_EXTRA", "").split()      # e.g. -DPPK_LIBM_HEADING, -DPPK_TRACE for A/B builds
 
 
 def _source_hash():

@@ -468,58 +468,4 @@ inline int launch_adof_clear(unsigned int* scratch, unsigned char* const* flags,
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 
-inline int launch_adof(const KArgs& k0, cudaStream_t s) {
-  KArgs k = k0;
-  // staged row windows: live rows 0..39, reference rows 0..27 (+ one following row for the window slack)
-  if (k.B < kAdofRbRows) return PPK_ERR_SHAPE;
-  for (int j = 0; j < kAdofJ; ++j)
-    if (k.ids[0][j] >= kAdofRbRows) return PPK_ERR_SHAPE;
-  const bool compact = k.init_bal != nullptr;
-  for (int j = 0; j < kAdofNB; ++j)
-    if (k.bal_ids[j] >= (compact ? kAdofRbRows : kAdofInitRows)) return PPK_ERR_SHAPE;
-  if (k.paddle_body[0] >= kAdofRbRows || k.pelvis_body >= kAdofRbRows) return PPK_ERR_SHAPE;
-  const void* al[] = {k.rb, compact ? (const void*)k.init_bal : (const void*)k.init_rb, k.root, k.dof, k.init_dof, k.force};
-  bool bulk = k.B > kAdofRbRows;
-  for (const void* p : al) bulk = bulk && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
-  k.bulk_ok = bulk ? 1 : 0;
-  const size_t smem = (size_t)(compact ? AdofLayout<true>::kFloats : AdofLayout<false>::kFloats) * sizeof(float);
-  static SmemOptIn opt_full, opt_compact, opt_full_c, opt_compact_c;
-  if (!opt_full.ensure(adof_step_kernel<false, false>, AdofLayout<false>::kFloats * sizeof(float)) ||
-      !opt_compact.ensure(adof_step_kernel<true, false>, AdofLayout<true>::kFloats * sizeof(float)) ||
-      !opt_full_c.ensure(adof_step_kernel<false, true>, AdofLayout<false>::kFloats * sizeof(float)) ||
-      !opt_compact_c.ensure(adof_step_kernel<true, true>, AdofLayout<true>::kFloats * sizeof(float)))
-    return PPK_ERR_LAUNCH;
-  const bool fused_reset = (k.phases & PPK_PHASE_RESET) != 0 && !(k.phases & kPhaseDeferCounterClear);
-  const long long tiles = (k.n + kAdofTile - 1) / kAdofTile;
-  {
-    static int occ_c = 0, occ_f = 0, sms = 0;
-    int& occ = compact ? occ_c : occ_f;
-    if (occ == 0) {
-      int dev = 0, o = 0, n_sm = 0;
-      const bool ok = cudaGetDevice(&dev) == cudaSuccess &&
-                      (compact ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, adof_step_kernel<true, false>, kAdofThreads, smem)
-                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, adof_step_kernel<false, false>, kAdofThreads, smem)) == cudaSuccess &&
-                      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && o > 0 && n_sm > 0;
-      if (ok) { occ = o; sms = n_sm; } else cudaGetLastError();
-    }
-    static int stag = -1;
-    if (stag < 0) {
-      const char* e = getenv("PPK_STAGGER_ADOF");
-      stag = e ? atoi(e) : 600;
-      if (stag < 0) stag = 0;
-    }
-    k.num_sms = sms > 0 ? sms : 1;
-    k.first_wave = occ * sms;
-    k.stagger = (occ > 0 && tiles > (long long)occ * sms) ? stag : 0;
-  }
-  const bool clip = k.clip_obs > 0.0f;
-  if (compact && !clip) adof_step_kernel<true, false><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
-  else if (compact) adof_step_kernel<true, true><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
-  else if (!clip) adof_step_kernel<false, false><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
-  else adof_step_kernel<false, true><<<(unsigned)tiles, kAdofThreads, smem, s>>>(k);
-  if (cudaGetLastError() != cudaSuccess) return PPK_ERR_LAUNCH;
-  if (fused_reset) return launch_adof_clear(k.scratch, k.flags, k.n, s);
-  return PPK_OK;
-}
-
 }  // namespace ppk

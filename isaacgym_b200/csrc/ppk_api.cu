@@ -9,6 +9,7 @@
 #include "ppk_family.cuh"
 #include "ppk_misc.cuh"
 #include "ppk_adof.cuh"
+#include "ppk_adof2.cuh"
 #include "ppk_policy.cuh"
 
 using namespace ppk;

@@ -76,6 +76,12 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Named barriers 1..15 (0 is __syncthreads): `threads` = arrivers + waiters.  A bar.sync completes only when EVERY expected
+// thread has arrived, so a barrier shared by several waiting warps makes each of them wait for the others: give every
+// waiting warp its own barrier id.
+__device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void bar_wait(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

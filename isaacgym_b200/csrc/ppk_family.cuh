@@ -81,8 +81,6 @@ struct FamilyLayout {
 //   1  heading table ready: warp 0 arrives, warp 3 waits        } one barrier per waiting warp: a waiter must never
 //   3  heading table ready: warp 0 arrives, warp 2 waits        } wait for ANOTHER waiter's arrival
 //   2  pre-reset state read: warp 1 arrives, warp 2 waits before it overwrites the staged rows of resetting envs
-__device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-__device__ __forceinline__ void bar_wait(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 constexpr int kResetBatch = 4;      // resetting envs of a tile whose source rows are in flight at once
 

@@ -134,6 +134,11 @@ def test_unfused_reference_call_sequence_equals_fused(variant):
     b.post_physics_step()
     torch.cuda.synchronize()
     for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf") + cfg.flag_names + cfg.counter_names + cfg.state_names:
+        if variant == "adof" and name == "rew_buf":
+            # ADOF's fused step and its single-phase calls are two kernels (ppk_adof2.cuh / ppk_adof.cuh) that add the
+            # 23 / 27 terms of the imitation sums in different orders: the reward agrees to fp32 rounding, not bitwise
+            torch.testing.assert_close(a.rew_buf, b.rew_buf, rtol=2e-6, atol=2e-6 * 3000.0)
+            continue
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert torch.equal(a.root_states, b.root_states) and torch.equal(a.vec_dof_states, b.vec_dof_states)
 
@@ -363,6 +368,11 @@ def test_adof_compact_reference_pose(n):
     del comp["initial_body_states"]                      # the compact tensor alone is enough
     run(cfg, comp, N.PHASE_ALL)
     for name in ("obs_buf", "rew_buf") + STATE_EXACT + cfg.flag_names + cfg.counter_names:
+        if name == "rew_buf":
+            # the compact pose runs on the second ADOF design for full tiles (ppk_adof2.cuh), the uncompacted one on the
+            # first: same terms, different summation order of the imitation sums
+            torch.testing.assert_close(comp[name], full[name], rtol=2e-6, atol=2e-6 * 3000.0)
+            continue
         assert torch.equal(comp[name], full[name]), name
     assert_exact(cfg, comp, want, STATE_EXACT + cfg.flag_names + cfg.counter_names, f"adof compact n={n}")
     check_fields(cfg, comp, want, f"adof compact n={n}")
@@ -662,6 +672,23 @@ def test_host_session_launch_table_is_a_per_step_input(variant, pin):
         assert int(dev["reset_buf"].sum()) > 0
     finally:
         sess.close()
+
+
+def test_adof_first_design_still_passes():
+    """ADOF's full fused step runs on ppk_adof2.cuh; tail envs, other phase subsets and unaligned tensors stay on the
+    first design (ppk_adof.cuh).  PPK_ADOF_V1=1 (read once per process) forces every env onto the first design."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("PPK_ADOF_V1") is not None:
+        pytest.skip("already inside the forced run")
+    env = dict(os.environ, PPK_ADOF_V1="1")
+    here = os.path.abspath(__file__)
+    out = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-k",
+                          "(test_fused_step_matches_oracle or test_ragged_sizes or test_multi_step_trajectory or "
+                          "test_golden_step_fixture or test_golden_vectors or test_adof_compact_reference_pose) and adof"],
+                         env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(here)))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
 
 
 def test_small_batches_also_pass_on_the_32_env_tiles():
