@@ -80,6 +80,15 @@ def test_argument_validation_returns_error_codes(lib):
     assert lib.ppk_post_physics_step(task, buf2, N.PHASE_ALL & ~N.PHASE_STATS, None) == -3  # PPK_ERR_ALIGN
     with pytest.raises(RuntimeError):
         N.check(-2, "x")
+    # PPK_PHASE_MOMENTS: needs PPK_PHASE_OBS, a moments buffer, and a variant of the family kernel
+    buf2.progress_buf = 0x1000
+    assert lib.ppk_post_physics_step(task, buf2, N.PHASE_ALL | N.PHASE_MOMENTS, None) == -1          # obs_moments NULL
+    buf2.obs_moments = 0x1004
+    assert lib.ppk_post_physics_step(task, buf2, N.PHASE_ALL | N.PHASE_MOMENTS, None) == -3          # not 8-byte aligned
+    buf2.obs_moments = 0x1000
+    assert lib.ppk_post_physics_step(task, buf2, N.PHASE_REWARD | N.PHASE_MOMENTS, None) == -4       # without PHASE_OBS
+    assert lib.ppk_post_physics_step(N.make_task(CONFIGS["adof"]), buf2, N.PHASE_ALL | N.PHASE_MOMENTS, None) == -4
+    assert lib.ppk_post_physics_step(task, buf2, 64, None) == -4                                      # unknown phase bit
 
 
 def test_task_descriptor_follows_the_reference_configs():
