@@ -513,7 +513,7 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_env": algo, "peak_source": peak_src,
-                     "kernel": f"family_step_kernel<{variant}>" if variant not in ("base", "adof") else f"{variant}_step_kernel",
+                     "kernel": {"base": "base_step_kernel", "adof": "adof2_step_kernel"}.get(variant, f"family_step_kernel<{variant}>"),
                      "note": "achieved = algorithmic bytes per launch / (CUDA-event time of the timed region / launches). "
                              "traffic = dram__bytes_read + dram__bytes_write of one launch from the committed ncu capture "
                              "(profiles/ncu_traffic.json): the AoS rows are 52 B, the TMA engine fetches 64-B granules, and most "
