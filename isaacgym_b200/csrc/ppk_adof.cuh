@@ -464,8 +464,11 @@ inline int launch_adof_clear(unsigned int* scratch, unsigned char* const* flags,
   long long cb = (n / 4 + 255) / 256;
   if (cb < 1) cb = 1;
   if (cb > sm_count() * 8) cb = sm_count() * 8;
-  adof_clear_counters_kernel<<<(unsigned)cb, 256, 0, s>>>(scratch, flags[4], flags[5], flags[6], flags[7], flags[8], n);
-  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+  if (launch_pdl(adof_clear_counters_kernel, (unsigned)cb, 256u, 0, s, scratch, flags[4], flags[5], flags[6], flags[7], flags[8], n) != cudaSuccess) {
+    cudaGetLastError();
+    return PPK_ERR_LAUNCH;
+  }
+  return PPK_OK;
 }
 
 }  // namespace ppk

@@ -77,6 +77,7 @@ adof2_step_kernel(const __grid_constant__ KArgs k) {
   const float clip = CLIP ? k.clip_obs : 0.0f;
   const int root_id = k.ids[0][0];
   const bool stats = (k.phases & PPK_PHASE_STATS) != 0;
+  gdc_wait();             // programmatic dependent launch: everything above ran while the previous kernel drained
   // every warp that needs the env's progress reads it HERE, before the barrier below: warp 0 rewrites it at the end
   const long long prog_in = k.progress[env0 + e8];
 
@@ -111,6 +112,8 @@ adof2_step_kernel(const __grid_constant__ KArgs k) {
   }
   __syncthreads();        // the initialised barriers are visible to every waiter
   PPK_STAMP(1);
+  gdc_launch_dependents();      // every CTA of the grid is scheduled by the time the last one gets here: the next kernel of the
+                                // stream may fill the slots the tail leaves empty and run its prologue (blocks in gdc_wait)
 
   // named barriers: 1..4 "heading table ready" (warp 0 arrives, ONE waiting warp each: 1, 2, 3, 5);
   //                 5 "per-env sums ready" (warps 1, 2, 4 arrive, warp 0 waits)
@@ -605,9 +608,9 @@ inline int launch_adof(const KArgs& k0, cudaStream_t s) {
     k2.n = tiles * kAdofTile;
     static int occ2 = 0, sms2 = 0;
     adof_soft_start(k2, adof2_step_kernel<false>, kAdof2Threads, smem2, tiles, occ2, sms2);
-    if (k.clip_obs > 0.0f) adof2_step_kernel<true><<<(unsigned)tiles, kAdof2Threads, smem2, s>>>(k2);
-    else adof2_step_kernel<false><<<(unsigned)tiles, kAdof2Threads, smem2, s>>>(k2);
-    if (cudaGetLastError() != cudaSuccess) return PPK_ERR_LAUNCH;
+    const cudaError_t le = (k.clip_obs > 0.0f) ? launch_pdl(adof2_step_kernel<true>, (unsigned)tiles, kAdof2Threads, smem2, s, k2)
+                                               : launch_pdl(adof2_step_kernel<false>, (unsigned)tiles, kAdof2Threads, smem2, s, k2);
+    if (le != cudaSuccess) { cudaGetLastError(); return PPK_ERR_LAUNCH; }
     done = k2.n;
   }
   if (done < k.n) {

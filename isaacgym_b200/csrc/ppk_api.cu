@@ -253,8 +253,11 @@ int launch_family(const KArgs& k0, cudaStream_t s) {
   k.num_sms = sms > 0 ? sms : 1;
   k.first_wave = occ * sms;
   k.stagger = (occ > 0 && tiles > (long long)occ * sms) ? stagger_cycles(smem) : 0;
-  kern<<<(unsigned)tiles, kFamilyThreads, smem, s>>>(k, m_span, m_row0);
-  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+  if (launch_pdl(kern, (unsigned)tiles, kFamilyThreads, smem, s, k, m_span, m_row0) != cudaSuccess) {
+    cudaGetLastError();
+    return PPK_ERR_LAUNCH;
+  }
+  return PPK_OK;
 }
 
 }  // namespace

@@ -82,6 +82,13 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void bar_wait(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization attribute
+// may START while the kernel before it in the stream is still draining; gdc_wait() blocks until that kernel has
+// completed and its memory is visible (a no-op for a plain launch), gdc_launch_dependents() lets the NEXT kernel of the
+// stream start early once every CTA of this one has called it (or exited).
+__device__ __forceinline__ void gdc_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void gdc_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

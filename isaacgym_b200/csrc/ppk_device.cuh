@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/ppk.h"
 
@@ -40,6 +41,33 @@ inline int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+// PPK_PDL=0 turns programmatic dependent launch of the step kernels off (A/B runs); default on
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PPK_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// Launch `kern` so that it may start while the previous kernel of the stream drains (the kernel itself calls gdc_wait()
+// before its first global access); falls back to a plain launch when PDL is off.
+template <class... KP, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KP...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KP(args)...);
 }
 
 constexpr int kRow = 13;  // floats per rigid-body / root-state row: pos3 quat4 linvel3 angvel3

@@ -119,6 +119,9 @@ family_step_kernel(const __grid_constant__ KArgs k, const __grid_constant__ CUte
 
   // ---- stage ---------------------------------------------------------------------------------------
   PPK_STAMP(0);
+  // Programmatic dependent launch: up to here (parameters, address arithmetic) the CTA may run while the previous kernel
+  // of the stream is still draining; nothing of global memory has been touched yet.
+  gdc_wait();
   if (fast) {
     if (warp == 0) {
       // one elected lane of the converged warp 0 sets the barriers up and issues the seven copies (warp-uniform
@@ -174,6 +177,9 @@ family_step_kernel(const __grid_constant__ KArgs k, const __grid_constant__ CUte
     __syncthreads();
   }
   PPK_STAMP(1);
+  // Every CTA of this grid has been scheduled once the last one gets here: from then on the next kernel of the stream may
+  // fill the slots the tail of this grid leaves empty and run its prologue (it blocks in gdc_wait until this grid is done).
+  gdc_launch_dependents();
 
   const float clip = k.clip_obs;
   const bool clip_on = clip > 0.0f;

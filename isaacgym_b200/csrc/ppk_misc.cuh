@@ -1,5 +1,6 @@
 // Small kernels around the fused step: BASE variant, pre_physics_step, reset_idx, statistics.
 #pragma once
+#include "ppk_async.cuh"
 #include "ppk_device.cuh"
 
 namespace ppk {
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(256)
 pre_step_kernel(float* __restrict__ actions, float clip, const float* __restrict__ offset, const float* __restrict__ scale,
                 float* __restrict__ pd, long long n, int D, const float* __restrict__ root, int rootN, int ball,
                 float* __restrict__ pre, int pre_stride, int pre_vx, int pre_vz, int* __restrict__ reset_count) {
+  // (launched plainly: as a programmatic dependent this kernel and the step kernel behind it measured 1.5 % slower)
   // the compacted reset lists of the coming post_physics_step start empty (no extra memset node)
   if (reset_count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *reset_count = 0;
   const long long total = n * D;
@@ -284,6 +286,8 @@ adof_clear_counters_kernel(unsigned int* any_reset, unsigned char* c0, unsigned 
   // reads the flag, then takes a ticket; the last one re-arms both words for the next step, so no
   // memset node is needed in front of the step kernel.
   __shared__ unsigned int flag_s;
+  gdc_wait();
+  gdc_launch_dependents();
   if (threadIdx.x == 0) flag_s = any_reset[0];
   __syncthreads();
   const bool clear = flag_s != 0u;
