@@ -339,6 +339,9 @@ def time_steps(tasks, steps, warmup, with_pre, log_every, world, dist):
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     folds = sum(1 for i in range(steps) if is_log(i))
     eager = world > 1 and not in_graph_collective and folds > 0
+    # keep the GPU busy (~100 us) while the host enqueues the start event and the first graph launch: the timed region
+    # then holds device time of the K steps, not the host's cudaGraphLaunch latency (8 us against 300 us at --steps 20)
+    torch.cuda._sleep(200000)
     start.record()
     for first, cnt in segs:
         graphs[(first % sets, cnt, first % period)].replay()
