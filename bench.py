@@ -258,6 +258,7 @@ def time_steps(tasks, steps, warmup, with_pre, log_every, world, dist):
     side = torch.cuda.Stream(dev)
     local = torch.zeros(N.PPK_NUM_STATS, dtype=torch.float64, device=dev)
     total = torch.zeros(N.PPK_NUM_STATS, dtype=torch.float64, device=dev)
+    align = torch.zeros(1, dtype=torch.float32, device=dev)
 
     def one_step(i, log):
         t = tasks[i % sets]
@@ -342,6 +343,11 @@ def time_steps(tasks, steps, warmup, with_pre, log_every, world, dist):
     # keep the GPU busy (~100 us) while the host enqueues the start event and the first graph launch: the timed region
     # then holds device time of the K steps, not the host's cudaGraphLaunch latency (8 us against 300 us at --steps 20)
     torch.cuda._sleep(200000)
+    if world > 1:
+        # device-side start line: the ranks' streams leave this tiny all-reduce together, so the timed region of a
+        # rank whose host came out of the barrier early does not include waiting (inside the captured collective)
+        # for a rank whose host came out late -- measured at N=8: up to 1.5 ms of such skew on the first region
+        dist.all_reduce(align, op=dist.ReduceOp.SUM)
     start.record()
     for first, cnt in segs:
         graphs[(first % sets, cnt, first % period)].replay()
@@ -357,6 +363,7 @@ def time_steps(tasks, steps, warmup, with_pre, log_every, world, dist):
         dist.barrier()
     torch.cuda.synchronize()
     sec = start.elapsed_time(end) / 1e3
+    time_steps.rank_sec = sec
     if world > 1:
         t = torch.tensor([sec], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
