@@ -39,12 +39,19 @@ struct Adof2Layout {
   static constexpr int kOffDof = kOffRoot + T * kRoot;                  // 5784
   static constexpr int kOffIDof = kOffDof + T * kDof;                   // 6216
   static constexpr int kOffForce = kOffIDof + T * kDof;                 // 6648
-  static constexpr int kOffRow0 = kOffForce + T * kAdofD;               // 6864: [T][16] windows around row ids[0]
-  static constexpr int kOffHd = kOffRow0 + T * 16;                      // 6992: [T][8] a0, sz, cw, -, root pos xyz, -
-  static constexpr int kOffPart = kOffHd + T * 8;                       // 7056: [3 warps][T][4] partial sums
-  static constexpr int kOffObs = kOffPart + 3 * T * 4;                  // 7152
-  static constexpr int kOffBar = kOffObs + T * kAdofObs;                // 9656
-  static constexpr int kFloats = kOffBar + 4;
+  static constexpr int kOffHd = kOffForce + T * kAdofD;                 // 6864: [T][8] a0, sz, cw, -, root pos xyz, -
+  static constexpr int kOffObs = kOffHd + T * 8;                        // 6928
+  static constexpr int kOffBar = kOffObs + T * kAdofObs;                // 9432
+  static constexpr int kFloats = kOffBar + 4;                           // 37 744 B: six CTAs per SM
+  // Two regions live inside others (224 floats less = the sixth resident CTA):
+  //  * the [T][16] windows around row ids[0] sit in env 0's imitation columns of the obs tile: they are consumed by
+  //    warp 0 before it arrives on the heading barriers 1..4, and the warps that write those columns (1, 2) wait on them;
+  //  * the per-env partial sums of warps 1, 2, 4 overwrite the first floats of what that warp alone has just consumed
+  //    (its half of the env's reference bodies / the env's DOF forces), after a __syncwarp.
+  static constexpr int kOffRow0 = kOffObs + 128;
+  static constexpr int kPartW2 = 12 * 6;                                // warp 2's reference bodies start here (body 12)
+  static_assert(6 * 11 + 2 * kAdofD + 7 <= 128 && 128 + T * 16 <= 6 * 11 + 2 * kAdofD + 7 + 6 * kAdofNB,
+                "the row windows stay inside the imitation columns");
   static constexpr uint32_t kTx = 4u * T * (kRbEnv + kInitEnv + kRoot + 2 * kDof + kAdofD);
   static_assert(kOffInit % 4 == 0 && kOffRoot % 4 == 0 && kOffDof % 4 == 0 && kOffIDof % 4 == 0 && kOffForce % 4 == 0 &&
                     kOffRow0 % 4 == 0 && kOffHd % 4 == 0 && kOffObs % 4 == 0 && kOffBar % 2 == 0,
@@ -55,7 +62,7 @@ struct Adof2Layout {
 };
 
 template <bool CLIP>
-__global__ void __launch_bounds__(kAdof2Threads, 5)
+__global__ void __launch_bounds__(kAdof2Threads, 6)
 adof2_step_kernel(const __grid_constant__ KArgs k) {
   using L = Adof2Layout;
   constexpr int T = L::T, D = kAdofD, J = kAdofJ, NB = kAdofNB;
@@ -71,7 +78,6 @@ adof2_step_kernel(const __grid_constant__ KArgs k) {
   float* force_s = smem + L::kOffForce;
   float* row0_s = smem + L::kOffRow0;
   float4* hd_s = reinterpret_cast<float4*>(smem + L::kOffHd);
-  float* part_s = smem + L::kOffPart;
   float* obs_s = smem + L::kOffObs;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   const float clip = CLIP ? k.clip_obs : 0.0f;
@@ -188,9 +194,9 @@ adof2_step_kernel(const __grid_constant__ KArgs k) {
     f_dpc = f_dpc || low;
     f_hdc = f_hdc || (pelvis_z < 0.97f);
     bar_wait(5, 128);       // the sums of warps 1, 2 (balance bodies) and 4 (DOFs)
-    const float* p1 = part_s + (0 * T + e8) * 4;
-    const float* p2 = part_s + (1 * T + e8) * 4;
-    const float* p4 = part_s + (2 * T + e8) * 4;
+    const float* p1 = init_s + e8 * L::kInitEnv;
+    const float* p2 = init_s + e8 * L::kInitEnv + L::kPartW2;
+    const float* p4 = force_s + e8 * D;
     const float sum_dp2 = p1[0] + p2[0], sum_dv2 = p1[1] + p2[1], sum_nrm = p1[2] + p2[2];
     const float sum_dq22 = p4[0], sum_dq5 = p4[1], sum_dqd22 = p4[2], sum_pow = p4[3];
     // compute_imitation_reward, is_g1 branch (ADOF:1330-1418)
@@ -276,8 +282,9 @@ adof2_step_kernel(const __grid_constant__ KArgs k) {
     s_dp2 += __shfl_xor_sync(0xffffffffu, s_dp2, 8); s_dp2 += __shfl_xor_sync(0xffffffffu, s_dp2, 16);
     s_dv2 += __shfl_xor_sync(0xffffffffu, s_dv2, 8); s_dv2 += __shfl_xor_sync(0xffffffffu, s_dv2, 16);
     s_nrm += __shfl_xor_sync(0xffffffffu, s_nrm, 8); s_nrm += __shfl_xor_sync(0xffffffffu, s_nrm, 16);
+    __syncwarp();                                         // every lane has its reference bodies in registers
     if (lane < T) {
-      float* p = part_s + ((warp - 1) * T + e8) * 4;
+      float* p = init_s + e8 * L::kInitEnv + ((warp == 1) ? 0 : L::kPartW2);
       p[0] = s_dp2; p[1] = s_dv2; p[2] = s_nrm;
     }
     bar_arrive(5, 128);
@@ -367,8 +374,9 @@ adof2_step_kernel(const __grid_constant__ KArgs k) {
     s_dq5 += __shfl_xor_sync(0xffffffffu, s_dq5, 8); s_dq5 += __shfl_xor_sync(0xffffffffu, s_dq5, 16);
     s_dqd22 += __shfl_xor_sync(0xffffffffu, s_dqd22, 8); s_dqd22 += __shfl_xor_sync(0xffffffffu, s_dqd22, 16);
     s_pow += __shfl_xor_sync(0xffffffffu, s_pow, 8); s_pow += __shfl_xor_sync(0xffffffffu, s_pow, 16);
+    __syncwarp();                                         // every lane has its forces in registers
     if (lane < T) {
-      float* p = part_s + (2 * T + e8) * 4;
+      float* p = force_s + e8 * D;
       p[0] = s_dq22; p[1] = s_dq5; p[2] = s_dqd22; p[3] = s_pow;
     }
     bar_arrive(5, 128);
