@@ -320,6 +320,16 @@ PPK_API int ppk_linear_pack(const float* weight /*[units,width]*/, const float* 
 PPK_API int ppk_policy_first_layer(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, int32_t width,
                                    const void* packed, int32_t units, int32_t activation, void* out_f16, void* stream);
 
+/* The same layer as the ROLLOUT forward computes it (rl_games get_action_values: no autocast, fp32):
+ * out[rows,units] fp32 = act(norm(obs) @ W^T + b) with every product formed from TF32 hi/lo splits of both operands
+ * (3 tensor-core MMAs, fp32 accumulation): within ~1e-6 * sum_k |x_k w_k| of an fp32 FMA chain.  Weights are packed
+ * once into hi/lo TF32 operand tiles (8 bytes per element).  units % 256 == 0; width <= 95 (24, 80, 94). */
+PPK_API size_t ppk_linear_packed_bytes_f32(int32_t units, int32_t width);
+PPK_API int ppk_linear_pack_f32(const float* weight /*[units,width]*/, const float* bias /*[units] or NULL*/, int32_t units,
+                                int32_t width, void* packed, size_t packed_bytes, void* stream);
+PPK_API int ppk_policy_first_layer_f32(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, int32_t width,
+                                       const void* packed, int32_t units, int32_t activation, float* out_f32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,6 +141,12 @@ def load():
     lib.ppk_policy_first_layer.restype = C.c_int
     lib.ppk_policy_first_layer.argtypes = [rp, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                            C.c_void_p, C.c_void_p]
+    lib.ppk_linear_packed_bytes_f32.restype = C.c_size_t
+    lib.ppk_linear_packed_bytes_f32.argtypes = [C.c_int32, C.c_int32]
+    lib.ppk_linear_pack_f32.restype = C.c_int
+    lib.ppk_linear_pack_f32.argtypes = lib.ppk_linear_pack.argtypes
+    lib.ppk_policy_first_layer_f32.restype = C.c_int
+    lib.ppk_policy_first_layer_f32.argtypes = lib.ppk_policy_first_layer.argtypes
     if lib.ppk_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libppk.so ABI {lib.ppk_abi_version()} != binding ABI {ABI_VERSION}")
     _LIB = lib

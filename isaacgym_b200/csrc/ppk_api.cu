@@ -11,6 +11,7 @@
 #include "ppk_adof.cuh"
 #include "ppk_adof2.cuh"
 #include "ppk_policy.cuh"
+#include "ppk_policy_f32.cuh"
 
 using namespace ppk;
 
@@ -618,6 +619,123 @@ int ppk_policy_first_layer(const PpkRunningMeanStd* rms, const float* obs, int64
     case 96: return launch_first_layer<96, 96>(k, s);       // TILT / NES / A3 / ALIGN (80) and A4 (94)
     case 320: return launch_first_layer<320, 64>(k, s);     // ADOF (313): weights streamed in K blocks of 64
     default: return PPK_ERR_SHAPE;
+  }
+}
+
+// ---- fp32 variant (rollout forward): 3 x TF32 split products, fp32 out ------------------------------------------
+extern "C++" {
+namespace {
+// default: single CTAs (202 us at 65 536 x 80 -> 2048, ELU).  PPK_FL32_CLUSTER=2: CTA pairs (cta_group::2, each CTA holds
+// half of the B operand): parity-green and half the weight bytes per SM, but the pair's MMAs run at half the single-CTA
+// rate with this operand layout (321 us), kept for A/B runs.  Process-wide: the packed weight layout depends on it.
+int f32_cluster_size() {
+  static const int v = [] { const char* e = getenv("PPK_FL32_CLUSTER"); return (e != nullptr && atoi(e) == 2) ? 2 : 1; }();
+  return v;
+}
+}  // namespace
+}  // extern "C++"
+
+size_t ppk_linear_packed_bytes_f32(int32_t units, int32_t width) {
+  if (units <= 0 || width <= 0 || units % kFlN != 0) return 0;
+  return (size_t)units * f32_kpad(width) * 2 * sizeof(float);
+}
+
+int ppk_linear_pack_f32(const float* weight, const float* bias, int32_t units, int32_t width, void* packed, size_t packed_bytes,
+                        void* stream) {
+  if (!weight || !packed) return PPK_ERR_NULL;
+  const size_t need = ppk_linear_packed_bytes_f32(units, width);
+  if (need == 0 || packed_bytes < need) return PPK_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(packed) & 15u) return PPK_ERR_ALIGN;
+  linear_pack_f32_kernel<<<sm_count() * 2, 256, 0, static_cast<cudaStream_t>(stream)>>>(weight, bias, units, width, f32_kpad(width),
+                                                                                  f32_cluster_size(), static_cast<float*>(packed));
+  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+}
+
+extern "C++" {
+namespace {
+// out [rows, units] fp32 as a 2-D tensor; box = one epilogue warp's [32 rows x 32 units] tile, 128B swizzle
+int make_out_map_f32(CUtensorMap* m, void* out, long long rows, int units) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return PPK_ERR_CUDA;
+  const cuuint64_t dims[2] = {(cuuint64_t)units, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)units * sizeof(float)};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? PPK_OK
+             : PPK_ERR_CUDA;
+}
+
+template <int KP, int ACT, int CL>
+int launch_first_layer_f32_as(const F32Args& k, const CUtensorMap& out_map, cudaStream_t s) {
+  using L = F32Layout<KP>;
+  auto kern = first_layer_f32_kernel<KP, ACT, CL>;
+  static SmemOptIn opt;
+  if (!opt.ensure(kern, L::kBytes)) return PPK_ERR_LAUNCH;
+  const long long groups = ((k.rows + kFlM - 1) / kFlM + CL - 1) / CL;
+  const long long units = groups * (k.units / kFlN);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kF32Threads);
+  cfg.dynamicSmemBytes = L::kBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  // persistent: as many clusters as can be resident at once (one CTA per SM; GPCs with an odd SM count leave one out)
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    int n = 0;
+    cfg.gridDim = dim3((unsigned)(sm_count() / CL * CL));
+    if (CL > 1) { if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); return PPK_ERR_LAUNCH; } }
+    else n = sm_count();
+    max_clusters = n;
+  }
+  const long long clusters = units < max_clusters ? units : max_clusters;
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  if (cudaLaunchKernelEx(&cfg, kern, k, out_map) != cudaSuccess) { cudaGetLastError(); return PPK_ERR_LAUNCH; }
+  return PPK_OK;
+}
+
+template <int KP>
+int launch_first_layer_f32(const F32Args& k, int activation, cudaStream_t s) {
+  CUtensorMap out_map;
+  int rc = make_out_map_f32(&out_map, k.out, k.rows, k.units);
+  if (rc != PPK_OK) return rc;
+  const bool pair = f32_cluster_size() == 2;
+  if (activation == PPK_ACT_ELU) return pair ? launch_first_layer_f32_as<KP, 1, 2>(k, out_map, s) : launch_first_layer_f32_as<KP, 1, 1>(k, out_map, s);
+  return pair ? launch_first_layer_f32_as<KP, 0, 2>(k, out_map, s) : launch_first_layer_f32_as<KP, 0, 1>(k, out_map, s);
+}
+}  // namespace
+}  // extern "C++"
+
+int ppk_policy_first_layer_f32(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, int32_t width, const void* packed,
+                               int32_t units, int32_t activation, float* out_f32, void* stream) {
+  F32Args k;
+  memset(&k, 0, sizeof(k));
+  if (rms != nullptr) {
+    int rc = rms_args(rms, &k.rms);
+    if (rc != PPK_OK) return rc;
+    if (rms->width != width) return PPK_ERR_SHAPE;
+  }
+  if (rows < 0 || width <= 0 || units <= 0 || units % kFlN != 0) return PPK_ERR_SHAPE;
+  if (activation != PPK_ACT_NONE && activation != PPK_ACT_ELU) return PPK_ERR_VARIANT;
+  if (rows == 0) return PPK_OK;
+  if (!obs || !packed || !out_f32) return PPK_ERR_NULL;
+  if ((reinterpret_cast<uintptr_t>(packed) & 15u) || (reinterpret_cast<uintptr_t>(out_f32) & 15u) ||
+      (reinterpret_cast<uintptr_t>(obs) & 3u))
+    return PPK_ERR_ALIGN;
+  k.obs = obs; k.rows = rows; k.width = width; k.units = units;
+  k.packed = static_cast<const unsigned char*>(packed);
+  k.out = out_f32;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (f32_kpad(width)) {
+    case 32: return launch_first_layer_f32<32>(k, activation, s);       // BASE (24)
+    case 88: return launch_first_layer_f32<88>(k, activation, s);       // TILT / NES / A3 / ALIGN (80)
+    case 96: return launch_first_layer_f32<96>(k, activation, s);       // A4 (94)
+    default: return PPK_ERR_SHAPE;                                      // ADOF (313): the row tile does not fit
   }
 }
 

@@ -9,6 +9,8 @@ merges the batch moments and then returns the normalised, +-5-clamped input.
 `FirstLayer` is the first `nn.Linear(num_obs, units[0])` + activation of the MLP
 (`units: [2048, ...]`, `activation: elu`, yaml:29-30) as `torch.autocast(float16)` runs it under
 `mixed_precision: True` (yaml:50), fused with the normalisation: one tcgen05 kernel, fp16 output.
+`FirstLayer(..., precision="fp32")` is the same layer as the rollout forward runs it (no autocast): fp32 products from
+TF32 hi/lo splits on the tensor cores, fp32 output.
 
 CUDA only; every call goes through the C ABI of libppk.so.
 """
@@ -124,30 +126,40 @@ class FirstLayer:
     ACTIVATIONS = {"None": N.PPK_ACT_NONE, None: N.PPK_ACT_NONE, "elu": N.PPK_ACT_ELU}
 
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], activation="elu",
-                 running_mean_std: Optional[RunningMeanStd] = None):
+                 running_mean_std: Optional[RunningMeanStd] = None, precision: str = "autocast_fp16"):
         if weight.device.type != "cuda":
             raise RuntimeError("FirstLayer is CUDA-only (no CPU fallback)")
+        if precision not in ("autocast_fp16", "fp32"):
+            raise ValueError("precision is 'autocast_fp16' (learner forward) or 'fp32' (rollout forward)")
         self._lib = N.load()
         self.units, self.width = int(weight.shape[0]), int(weight.shape[1])
         self.activation = self.ACTIVATIONS[activation]
         self.rms = running_mean_std
-        nbytes = self._lib.ppk_linear_packed_bytes(self.units, self.width)
+        self.fp32 = precision == "fp32"
+        lib = self._lib
+        self._packed_bytes, self._pack, self._forward = (
+            (lib.ppk_linear_packed_bytes_f32, lib.ppk_linear_pack_f32, lib.ppk_policy_first_layer_f32) if self.fp32 else
+            (lib.ppk_linear_packed_bytes, lib.ppk_linear_pack, lib.ppk_policy_first_layer))
+        self.out_dtype = torch.float32 if self.fp32 else torch.float16
+        nbytes = self._packed_bytes(self.units, self.width)
         if nbytes == 0:
             raise ValueError("units must be a positive multiple of 256")
         self.packed = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
         w = weight.detach().to(torch.float32).contiguous()
         b = None if bias is None else bias.detach().to(torch.float32).contiguous()
-        N.check(self._lib.ppk_linear_pack(w.data_ptr(), None if b is None else b.data_ptr(), self.units, self.width,
-                                          self.packed.data_ptr(), nbytes, N.current_stream_ptr()), "linear_pack")
+        N.check(self._pack(w.data_ptr(), None if b is None else b.data_ptr(), self.units, self.width,
+                           self.packed.data_ptr(), nbytes, N.current_stream_ptr()), "linear_pack")
 
     def forward(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if obs.dtype != torch.float32 or not obs.is_contiguous() or obs.dim() != 2 or obs.shape[1] != self.width:
             raise ValueError(f"expected a contiguous float32 [rows,{self.width}] tensor")
         if out is None:
-            out = torch.empty(obs.shape[0], self.units, dtype=torch.float16, device=obs.device)
+            out = torch.empty(obs.shape[0], self.units, dtype=self.out_dtype, device=obs.device)
+        elif out.dtype != self.out_dtype or not out.is_contiguous() or tuple(out.shape) != (obs.shape[0], self.units):
+            raise ValueError(f"out must be a contiguous {self.out_dtype} [rows,{self.units}] tensor")
         rms = None if self.rms is None else self.rms._struct()
-        N.check(self._lib.ppk_policy_first_layer(rms, obs.data_ptr(), obs.shape[0], self.width, self.packed.data_ptr(),
-                                                 self.units, self.activation, out.data_ptr(), N.current_stream_ptr()),
+        N.check(self._forward(rms, obs.data_ptr(), obs.shape[0], self.width, self.packed.data_ptr(),
+                              self.units, self.activation, out.data_ptr(), N.current_stream_ptr()),
                 "policy_first_layer")
         return out
 

@@ -68,6 +68,18 @@ def first_layer(x_norm, weight, bias, activation="elu"):
     return y
 
 
+def first_layer_fp32(x_norm, weight, bias, activation="elu"):
+    """The rollout forward (no autocast): plain fp32 act(linear(x)) as torch computes it on the CPU.  Also returns the
+    scale of the rounding noise of the dot product, sum_k |x_k w_k| + |b|, that tolerances are stated against."""
+    y = F.linear(x_norm, weight, bias)
+    scale = x_norm.abs() @ weight.abs().t()
+    if bias is not None:
+        scale = scale + bias.abs()
+    if activation == "elu":
+        y = F.elu(y)
+    return y, scale
+
+
 def first_layer_torch_autocast(x_norm, weight, bias, activation="elu"):
     """The same through torch's own autocast machinery (CPU)."""
     with torch.autocast("cpu", dtype=torch.float16):

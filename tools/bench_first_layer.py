@@ -71,6 +71,21 @@ def main():
         t2 = timeit(torch_path, iters=30)
         print(json.dumps({"kernel": "torch: normalise + cuBLAS fp16 linear + elu (library baseline)", "rows": rows,
                           "units": units, "us": t2 * 1e6, "speedup_of_fused": t2 / t}))
+        if width <= 95:           # the fp32 (rollout-forward) variant: 3 x TF32 split products, fp32 out
+            layer32 = FirstLayer(w, b, "elu", rms, precision="fp32")
+            o32 = torch.empty(rows, units, dtype=torch.float32, device=dev)
+            t3 = timeit(lambda: layer32(nxt(), o32), iters=30)
+            bytes32 = rows * (width * 4 + units * 4)
+            print(json.dumps({"kernel": "first_layer_f32_kernel (normalise + 3xTF32 linear + elu, fp32 out)", "rows": rows,
+                              "units": units, "us": t3 * 1e6, "hbm_gbs": bytes32 / t3 / 1e9, "hbm_frac": bytes32 / t3 / 1e9 / PEAK,
+                              "tflops_tf32_issued": 3 * 2.0 * rows * ((width + 8) // 8 * 8) * units / t3 / 1e12}))
+
+            def torch_fp32():
+                x = torch.clamp((nxt() - mean) / den, -5.0, 5.0)
+                return torch.nn.functional.elu(torch.nn.functional.linear(x, w, b))
+            t4 = timeit(torch_fp32, iters=10)
+            print(json.dumps({"kernel": "torch: normalise + cuBLAS fp32 linear (TF32 off) + elu (library baseline)", "rows": rows,
+                              "units": units, "us": t4 * 1e6, "speedup_of_fused": t4 / t3}))
 
 
 if __name__ == "__main__":
