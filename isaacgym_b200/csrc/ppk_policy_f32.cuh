@@ -20,7 +20,9 @@
 // leader (rank 0) issues the MMAs; the peer's MMA warp forwards its CTA's "stage landed + K step of the row tile ready /
 // accumulator drained" events to barriers in the leader's shared memory, and the leader's commits are multicast to both
 // CTAs' barriers.  Parity-green, but measured slower (a pair MMA takes twice a single one with this operand layout), so
-// it is the A/B variant, not the default.
+// it is the A/B variant, not the default.  (Raw issue rate without operand waits, `-DPPK_F32_DBG=336`: 178 cycles per
+// M128 N256 K8 MMA, 367 per M256 pair MMA: the same per SM, ~70 % of the tensor pipe's rate, 85-88 us for the whole layer;
+// polling the remotely signalled barriers with test_wait instead of try_wait made the pair slower, not faster.)
 // Measured, 65 536 x 80 -> 2048, ELU (`gpurun_out/r2_f32_ab*.log`): 202 us (no activation: 178) = 2.7 TB/s of output; the
 // parts alone: epilogue + stores 129 us, weights + MMAs + row tiles 138 us; they share L2 bandwidth (180 KB of weights in,
 // 128 KB of output out per unit) and overlap to 6.4 us per unit.
@@ -28,7 +30,7 @@
 #include "ppk_policy.cuh"
 
 #ifndef PPK_F32_DBG
-#define PPK_F32_DBG 0       // A/B builds only: 2 no global stores, 4 no MMA, 16 no weight loads, 32 no staging writes, 64 no epilogue
+#define PPK_F32_DBG 0       // A/B builds only: 2 no global stores, 4 no MMA, 16 no weight loads, 32 no staging writes, 64 no epilogue, 256 no operand waits
 #endif
 
 namespace ppk {
@@ -444,9 +446,12 @@ first_layer_f32_kernel(const __grid_constant__ F32Args k, const __grid_constant_
         for (int kb = 0; kb < NKB; ++kb) {
           const long long bi = it * NKB + kb;
           const int sb = (int)(bi % R), phb = (int)((bi / R) & 1);
-          if (first_of_tile) mbar_wait(a_full + kb, (uint32_t)(j & 1));
-          mbar_wait(b_full + sb, phb);
-          if (CL > 1) {     // the peer's arrival says: its weight stage AND its K step of the row tile are in place
+          if (PPK_F32_DBG & 256) { if (!leader) continue; }     // raw MMA issue rate: no operand waits at all
+          else {
+            if (first_of_tile) mbar_wait(a_full + kb, (uint32_t)(j & 1));
+            mbar_wait(b_full + sb, phb);
+          }
+          if (CL > 1 && !(PPK_F32_DBG & 256)) {     // the peer's arrival says: its weight stage AND its K step of the row tile are in place
             if (!leader) { tc::mbar_arrive_remote(peer_b_full + sb, 0); continue; }
             tc::mbar_wait_cluster(peer_b_full + sb, phb);
           }
