@@ -30,7 +30,7 @@
 #include "ppk_policy.cuh"
 
 #ifndef PPK_F32_DBG
-#define PPK_F32_DBG 0       // A/B builds only: 2 no global stores, 4 no MMA, 16 no weight loads, 32 no staging writes, 64 no epilogue, 256 no operand waits
+#define PPK_F32_DBG 0       // A/B builds only: 2 no global stores, 4 no MMA, 16 no weight loads, 32 no staging writes, 64 no epilogue, 256 no operand waits, 512 epilogue stores straight from registers (2.5x slower than the staged tensor stores)
 #endif
 
 namespace ppk {
@@ -518,6 +518,15 @@ first_layer_f32_kernel(const __grid_constant__ F32Args k, const __grid_constant_
         if (ACT == 1) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = elu_f32(o[i]);
+        }
+        if (PPK_F32_DBG & 512) {          // A/B: straight from the registers, 16-byte pieces of the lane's own output row
+          const long long row = mt * kFlM + q * 32 + lane;
+          if (row < k.rows) {
+            float4* dst = reinterpret_cast<float4*>(k.out + row * k.units + col0 + gi * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) __stcs(dst + i, make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+          }
+          return;
         }
         // the tensor store of the previous group has finished reading the tile
         if (lane == 0) tc::bulk_wait_read0();
