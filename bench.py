@@ -158,9 +158,14 @@ def run_learner_side(tasks, units, peak, iters=40, warm=5):
     b = torch.randn(units, device=dev, generator=g) * 0.1
     layer = FirstLayer(w, b, "elu", rms)
     out = torch.empty(rows, units, dtype=torch.float16, device=dev)
+    kinds = [("rms_update", lambda o: rms.update(o)), ("first_layer", lambda o: layer(o, out))]
+    if width <= 95:          # the rollout forward's fp32 variant (3 x TF32 split products, fp32 out)
+        layer32 = FirstLayer(w, b, "elu", rms, precision="fp32")
+        out32 = torch.empty(rows, units, dtype=torch.float32, device=dev)
+        kinds.append(("first_layer_fp32", lambda o: layer32(o, out32)))
     res = {}
-    for name, fn in (("rms_update", lambda o: rms.update(o)), ("first_layer", lambda o: layer(o, out))):
-        if name == "first_layer":
+    for name, fn in kinds:
+        if name != "rms_update":
             rms.eval()
         for i in range(warm):
             fn(obs[i % len(obs)])
@@ -172,7 +177,7 @@ def run_learner_side(tasks, units, peak, iters=40, warm=5):
         e1.record()
         torch.cuda.synchronize()
         sec = e0.elapsed_time(e1) * 1e-3 / iters
-        nbytes = rows * width * 4 + (rows * units * 2 if name == "first_layer" else 0)
+        nbytes = rows * width * 4 + rows * units * {"rms_update": 0, "first_layer": 2, "first_layer_fp32": 4}[name]
         res[name] = {"us": sec * 1e6, "rows_per_s": rows / sec, "achieved_gbs": nbytes / sec / 1e9,
                      "roofline_frac": nbytes / sec / 1e9 / peak}
     # the same update fed by the step kernel itself (PPK_PHASE_MOMENTS): step + fold vs step, then + separate update
@@ -222,6 +227,9 @@ def run_learner_side(tasks, units, peak, iters=40, warm=5):
     res["first_layer"].update({"units": units, "dtype": "f16 operands, f32 accumulate (tcgen05), f16 out",
                                "tflops": 2.0 * rows * width * units / (res["first_layer"]["us"] * 1e-6) / 1e12,
                                "bound": "hbm (the [rows, units] fp16 write)"})
+    if "first_layer_fp32" in res:
+        res["first_layer_fp32"].update({"units": units, "dtype": "3 x tf32 split products, f32 accumulate (tcgen05), f32 out",
+                                        "bound": "hbm (the [rows, units] fp32 write)"})
     return res
 
 
