@@ -460,7 +460,7 @@ int rms_launch_moments(const PpkRunningMeanStd* rms, const RmsArgs& a, const flo
   if (R < 1) R = 1;
   if (R < (vec ? 8 : 2)) R = (wx * (vec ? 8 : 2) <= 1024) ? (vec ? 8 : 2) : R;     // the fold needs 2*VEC row slots
   long long blocks = (rows + (long long)R * 4 - 1) / ((long long)R * 4);
-  if (blocks > sm_count()) blocks = sm_count();   // one CTA per SM
+  if (blocks > 2 * sm_count()) blocks = 2 * sm_count();   // two CTAs per SM: the whole batch is in flight in one pass
   if (blocks > kRmsMaxCtas) blocks = kRmsMaxCtas;
   if (blocks < 1) blocks = 1;
   const size_t smem = sizeof(double) * 2 * (vec ? 4 : 1) * R * wx;

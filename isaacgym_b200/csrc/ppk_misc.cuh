@@ -43,22 +43,46 @@ base_step_kernel(const __grid_constant__ KArgs k) {
   // reset_idx of the envs flagged by the PREVIOUS step's reward (BASE:589-591)
   const bool base_resets = (phases & PPK_PHASE_RESET) && on && k.reset[env] != 0;
   if (phases & PPK_PHASE_RESET) append_reset_indices(k, base_resets, env, lane);
-  // the warp resets its flagged envs one after the other, all lanes copying (coalesced rows instead of one
-  // lane walking 35 + 2*52 floats)
-  for (unsigned pending = __ballot_sync(0xffffffffu, base_resets); pending != 0; pending &= pending - 1) {
-    const long long e = env0 + (__ffs(pending) - 1);
-    const float* ir = k.init_root + (size_t)e * rootN;
-    float* go = k.root_out + (size_t)e * rootN;             // = the input rows unless the caller splits the reset output off
-    for (int f = lane; f < k.A * 7; f += 32) {              // pos + rot; velocities are NOT zeroed (BASE:533-534)
-      const int a = f / 7, c = f - a * 7;
-      go[a * kRow + c] = ir[a * kRow + c];
+  // the warp resets its flagged envs cooperatively, all lanes copying (coalesced rows instead of one lane walking
+  // 35 + 2*52 floats), four envs per pass with every load of the pass requested before the first store: with a tenth of
+  // the envs flagged (the synthetic states) a pass per env was three dependent DRAM round trips per warp
+  for (unsigned pending = __ballot_sync(0xffffffffu, base_resets); pending != 0;) {
+    constexpr int G = 4;
+    long long e[G];
+    bool live[G];
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      live[u] = pending != 0;
+      e[u] = env0 + (live[u] ? __ffs(pending) - 1 : 0);
+      pending &= pending - 1;               // 0 stays 0
     }
-    if (lane < 6)                                           // ball1 <- velocity_1, ball2 <- velocity_2 (BASE:549-550)
-      go[(k.ball + lane / 3) * kRow + 7 + lane % 3] = k.reset_vel[lane];
-    if (k.reset_dof) {                                      // BASE:552 (PpkTask.reset_dof; initial_dof_states required with it)
-      const float* id = k.init_dof + (size_t)e * 2 * k.D;
-      float* gd = k.dof_out + (size_t)e * 2 * k.D;
-      for (int i = lane; i < 2 * k.D; i += 32) gd[i] = id[i];
+    const int nroot = k.A * 7;              // pos + rot; velocities are NOT zeroed (BASE:533-534)
+    for (int f0 = 0; f0 < nroot; f0 += 32) {
+      const int f = f0 + lane;
+      const int a = f / 7, c = f - a * 7;
+      float v[G];
+#pragma unroll
+      for (int u = 0; u < G; ++u) v[u] = (live[u] && f < nroot) ? k.init_root[(size_t)e[u] * rootN + a * kRow + c] : 0.0f;
+#pragma unroll
+      for (int u = 0; u < G; ++u)
+        if (live[u] && f < nroot) k.root_out[(size_t)e[u] * rootN + a * kRow + c] = v[u];   // = the input rows unless the caller splits the reset output off
+    }
+    if (lane < 6) {                         // ball1 <- velocity_1, ball2 <- velocity_2 (BASE:549-550)
+      const float rv = k.reset_vel[lane];
+#pragma unroll
+      for (int u = 0; u < G; ++u)
+        if (live[u]) k.root_out[(size_t)e[u] * rootN + (k.ball + lane / 3) * kRow + 7 + lane % 3] = rv;
+    }
+    if (k.reset_dof) {                      // BASE:552 (PpkTask.reset_dof; initial_dof_states required with it)
+      for (int i0 = 0; i0 < 2 * k.D; i0 += 32) {
+        const int i = i0 + lane;
+        float v[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) v[u] = (live[u] && i < 2 * k.D) ? k.init_dof[(size_t)e[u] * 2 * k.D + i] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < G; ++u)
+          if (live[u] && i < 2 * k.D) k.dof_out[(size_t)e[u] * 2 * k.D + i] = v[u];
+      }
     }
   }
   __syncwarp();                                             // the observations below read the rows just written

@@ -51,8 +51,8 @@ __device__ __forceinline__ void rms_merge_column(const RmsArgs& a, double* sums,
   sums[a.width + c] = 0.0;
 }
 
-constexpr int kRmsMaxCtas = 256;      // upper bound of the grid (one CTA per SM, sm_count() at launch)
-constexpr int kRmsSlots = 8;          // copies of the 2W accumulators the CTAs' atomics are spread over
+constexpr int kRmsMaxCtas = 512;      // upper bound of the grid (two CTAs per SM, 2 * sm_count() at launch)
+constexpr int kRmsSlots = 16;         // copies of the 2W accumulators the CTAs' atomics are spread over
 
 // Column sums and sums of squares of obs [rows, width] in fp64.  VEC = 4: threadIdx.x owns four adjacent
 // columns (one 16-byte load per row), threadIdx.y walks the rows; eight rows in flight per thread.
