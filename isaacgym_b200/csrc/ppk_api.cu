@@ -503,8 +503,12 @@ int ppk_rms_fold_step_moments(const PpkRunningMeanStd* rms, double* obs_moments,
   if (rc != PPK_OK) return rc;
   if (!rms->moments || !obs_moments) return PPK_ERR_NULL;
   if (merge && !(batch_rows > 0.0)) return PPK_ERR_SHAPE;
-  rms_fold_step_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(a, rms->moments, obs_moments, batch_rows, merge);
-  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+  if (launch_pdl(rms_fold_step_kernel, 1u, 1024u, 0, static_cast<cudaStream_t>(stream), a, rms->moments, obs_moments, batch_rows,
+                 (int)merge) != cudaSuccess) {
+    cudaGetLastError();
+    return PPK_ERR_LAUNCH;
+  }
+  return PPK_OK;
 }
 
 int ppk_rms_update(const PpkRunningMeanStd* rms, const float* obs, int64_t rows, void* stream) {

@@ -155,22 +155,39 @@ __global__ void rms_merge_kernel(RmsArgs a, double* sums, double batch_rows) {
 
 // The column moments a step kernel left in PPK_MOMENT_SLOTS slot copies (PPK_PHASE_MOMENTS): fold them into sums[0..2W),
 // clear the slots, and (merge != 0) fold the batch into the running statistics.  One CTA: 2W <= 1024 sums of 64 doubles.
+// Launched as a programmatic dependent of the step kernel: it is resident, with the running statistics already in
+// registers, when the step's last CTA retires, and every slot value of a thread is requested at once -- the kernel is a
+// chain of L2 round trips (was: launch, count, three batches of slot loads, mean / var).
 __global__ void __launch_bounds__(1024)
 rms_fold_step_kernel(RmsArgs a, double* sums, double* slots, double batch_rows, int merge) {
-  // thread (g, c): column c of the 2W sums, slot copies g, g + G, ... (all loads of a thread in flight at once)
+  // thread (g, c): column c of the 2W sums, slot copies g, g + G, ...
   __shared__ double part[1024];
   const int width = a.width, cols = 2 * width;
   const int G = max(1, min((int)blockDim.x / cols, PPK_MOMENT_SLOTS));
-  const double count = *a.count;
   const int per = blockDim.x / G;                 // columns handled per pass
+  // the running statistics were written by an earlier rms kernel of the stream, which the step kernel ahead of this one
+  // has already waited for: they may be read before the dependency wait
+  const double count = *a.count;
+  double old_mean = 0.0, old_var = 0.0;
+  if (merge && (int)threadIdx.x < width) { old_mean = a.mean[threadIdx.x]; old_var = a.var[threadIdx.x]; }
+  gdc_wait();
   for (int c0 = 0; c0 < cols; c0 += per) {
     const int g = threadIdx.x / per, c = c0 + threadIdx.x % per;
     double tot = 0.0;
     if (g < G && c < cols) {
-#pragma unroll 4
-      for (int b = g; b < PPK_MOMENT_SLOTS; b += G) {
-        tot += __ldcg(slots + (size_t)b * cols + c);          // written by L2 atomics of the step kernel
-        slots[(size_t)b * cols + c] = 0.0;
+      constexpr int kBatch = 16;
+      for (int b0 = g; b0 < PPK_MOMENT_SLOTS; b0 += kBatch * G) {
+        double t[kBatch];
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+          const int b = b0 + i * G;
+          t[i] = b < PPK_MOMENT_SLOTS ? __ldcg(slots + (size_t)b * cols + c) : 0.0;       // written by L2 atomics of the step kernel
+        }
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+          const int b = b0 + i * G;
+          if (b < PPK_MOMENT_SLOTS) { tot += t[i]; slots[(size_t)b * cols + c] = 0.0; }
+        }
       }
     }
     part[threadIdx.x] = tot;
@@ -182,7 +199,25 @@ rms_fold_step_kernel(RmsArgs a, double* sums, double* slots, double batch_rows, 
     __syncthreads();
   }
   if (!merge) return;
-  for (int c = threadIdx.x; c < width; c += blockDim.x) rms_merge_column(a, sums, batch_rows, count, c);
+  __threadfence_block();
+  __syncthreads();
+  if (width <= (int)blockDim.x) {
+    const int c = threadIdx.x;
+    if (c < width) {            // rms_merge_column with the old statistics already here
+      const double S = sums[c], SS = sums[width + c];
+      const double bmean = S / batch_rows;
+      const double bvar = (SS - S * bmean) / (batch_rows - 1.0);
+      const double delta = bmean - old_mean;
+      const double tot = count + batch_rows;
+      const double m2 = old_var * count + bvar * batch_rows + delta * delta * count * batch_rows / tot;
+      a.mean[c] = old_mean + delta * batch_rows / tot;
+      a.var[c] = m2 / tot;
+      sums[c] = 0.0;
+      sums[width + c] = 0.0;
+    }
+  } else {
+    for (int c = threadIdx.x; c < width; c += blockDim.x) rms_merge_column(a, sums, batch_rows, count, c);
+  }
   if (threadIdx.x == 0) *a.count = count + batch_rows;
 }
 
