@@ -397,12 +397,16 @@ int ppk_pre_physics_step(const PpkTask* t, const PpkBuffers* b, void* stream) {
   if (b->num_envs < 0 || t->num_dofs <= 0) return PPK_ERR_SHAPE;
   if (b->num_envs == 0) return PPK_OK;
   const long long total = b->num_envs * t->num_dofs;
-  long long blocks = (total + 255) / 256;
-  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-  pre_step_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int vec = ((reinterpret_cast<uintptr_t>(b->actions) | reinterpret_cast<uintptr_t>(b->pd_targets)) & 15u) == 0;
+  const long long per_block = vec ? 1024 : 256;         // elements of the [N, D] tensors per CTA and pass
+  long long action_blocks = (total + per_block - 1) / per_block;
+  if (action_blocks > sm_count() * 32) action_blocks = sm_count() * 32;
+  long long ball_blocks = save_ball ? (b->num_envs + 255) / 256 : 0;       // one thread per env: every scattered read in flight at once
+  if (ball_blocks > sm_count() * 64) ball_blocks = sm_count() * 64;
+  pre_step_kernel<<<(unsigned)(action_blocks + ball_blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       b->actions, b->clip_actions, b->pd_action_offset, b->pd_action_scale, b->pd_targets, b->num_envs, t->num_dofs, b->root_states,
       t->num_actors * kRow, t->ball_actor, save_ball ? b->pre_ball_states : nullptr, b->pre_ball_stride,
-      b->pre_vx_offset, b->pre_vz_offset, b->reset_count);
+      b->pre_vx_offset, b->pre_vz_offset, b->reset_count, (unsigned)action_blocks, vec);
   return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
 }
 

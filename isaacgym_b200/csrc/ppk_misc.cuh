@@ -134,32 +134,60 @@ base_step_kernel(const __grid_constant__ KArgs k) {
 
 // ---- pre_physics_step (TILT:1002-1020) ---------------------------------------------------------------
 // pd_tar[n,d] = offset[d] + scale[d]*actions[n,d]; save the ball's vx (and vz) for the next reward.
+// CTAs [0, action_blocks) scale the actions, 16 bytes per thread and access when both tensors are 16-byte aligned (the
+// [N, D] tensors are flat arrays here); the remaining CTAs save the ball velocities (two 4-byte reads at a 156-byte stride
+// per env: a 64-byte granule fetched for 8 bytes, so this part is the larger half of the DRAM traffic) -- the two parts run
+// side by side instead of one after the other in every thread (131 072 envs: 9.1 -> 7.0 us; 1 M envs: 39 us for ~165 MB of
+// DRAM traffic, 67 MB of it the granules around the ball velocities).
 __global__ void __launch_bounds__(256)
 pre_step_kernel(float* __restrict__ actions, float clip, const float* __restrict__ offset, const float* __restrict__ scale,
                 float* __restrict__ pd, long long n, int D, const float* __restrict__ root, int rootN, int ball,
-                float* __restrict__ pre, int pre_stride, int pre_vx, int pre_vz, int* __restrict__ reset_count) {
+                float* __restrict__ pre, int pre_stride, int pre_vx, int pre_vz, int* __restrict__ reset_count,
+                unsigned action_blocks, int vec) {
   // (launched plainly: as a programmatic dependent this kernel and the step kernel behind it measured 1.5 % slower)
   // the compacted reset lists of the coming post_physics_step start empty (no extra memset node)
   if (reset_count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *reset_count = 0;
   const long long total = n * D;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    int d = (int)(i % D);
-    float a = ld_stream(actions + i);
-    if (clip > 0.0f) {                    // VecTask.step: torch.clamp(actions, -clip, clip), kept in self.actions
-      a = fminf(fmaxf(a, -clip), clip);
-      actions[i] = a;
+  if (blockIdx.x < action_blocks) {
+    const long long stride = (long long)action_blocks * blockDim.x;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long done = 0;                    // elements [0, done) are handled four at a time
+    if (vec) {
+      const long long n4 = total >> 2;
+      done = n4 << 2;
+      for (long long i4 = t0; i4 < n4; i4 += stride) {
+        float4 a4 = __ldcs(reinterpret_cast<const float4*>(actions) + i4);
+        float a[4] = {a4.x, a4.y, a4.z, a4.w}, o[4];
+        int d = (int)((i4 << 2) % D);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (clip > 0.0f) a[j] = fminf(fmaxf(a[j], -clip), clip);      // VecTask.step: torch.clamp(actions, -clip, clip), kept in self.actions
+          o[j] = __ldg(offset + d) + __ldg(scale + d) * a[j];
+          if (++d == D) d = 0;
+        }
+        if (clip > 0.0f) reinterpret_cast<float4*>(actions)[i4] = make_float4(a[0], a[1], a[2], a[3]);
+        __stcs(reinterpret_cast<float4*>(pd) + i4, make_float4(o[0], o[1], o[2], o[3]));
+      }
     }
-    st_stream(pd + i, offset[d] + scale[d] * a);
-  }
-  if (pre != nullptr) {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+    for (long long i = done + t0; i < total; i += stride) {
+      const int d = (int)(i % D);
+      float a = ld_stream(actions + i);
+      if (clip > 0.0f) {
+        a = fminf(fmaxf(a, -clip), clip);
+        actions[i] = a;
+      }
+      st_stream(pd + i, offset[d] + scale[d] * a);
+    }
+  } else if (pre != nullptr) {
+    const long long stride = (long long)(gridDim.x - action_blocks) * blockDim.x;
+    for (long long e = (long long)(blockIdx.x - action_blocks) * blockDim.x + threadIdx.x; e < n; e += stride) {
       const float* b = root + (size_t)e * rootN + ball * kRow;
       if (pre_stride == kRow) {          // the reference's full-row clone (TILT:1020)
         for (int c = 0; c < kRow; ++c) pre[(size_t)e * kRow + c] = b[c];
       } else {
-        pre[(size_t)e * pre_stride + pre_vx] = b[7];
-        if (pre_vz >= 0 && pre_vz != pre_vx) pre[(size_t)e * pre_stride + pre_vz] = b[9];
+        const float vx = __ldg(b + 7), vz = __ldg(b + 9);
+        pre[(size_t)e * pre_stride + pre_vx] = vx;
+        if (pre_vz >= 0 && pre_vz != pre_vx) pre[(size_t)e * pre_stride + pre_vz] = vz;
       }
     }
   }
