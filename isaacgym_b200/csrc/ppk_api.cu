@@ -218,7 +218,7 @@ bool small_batch(long long n) {
     forced = e ? atoi(e) : -1;
   }
   if (forced >= 0) return forced != 0;
-  return (n + 31) / 32 <= 15LL * sm_count();
+  return (n + 31) / 32 <= 21LL * sm_count();     // crossover measured between 98 304 (16-env tiles 1 % ahead) and 131 072 envs (32-env tiles 1 % ahead)
 }
 
 template <int V, int H, int J, int D, int A, int TILE>
