@@ -514,6 +514,12 @@ def main():
     sec, launches, totals = time_steps(tasks, args.steps, args.warmup, with_pre, cfg.log_every, world, dist)
     clocks = sampler.stop()
     stat_means = {name: x / (n * world) for name, x in zip(N.STAT_NAMES, totals)}   # the last logging step's all-reduced sums
+    rank_ms = None
+    if world > 1:        # every rank's own device time of the timed region (the line reports their maximum)
+        mine = torch.tensor([time_steps.rank_sec], dtype=torch.float64, device="cuda")
+        everyone = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(everyone, mine)
+        rank_ms = [round(1e3 * float(x.item()) / args.steps, 5) for x in everyone]
 
     total_envs = n * world
     value = total_envs * args.steps / sec
@@ -540,6 +546,8 @@ def main():
                              "payload": "8 doubles, all-reduce(SUM)", "mode": time_steps.collective_mode},
         "stats_sample": {k: stat_means[k] for k in ("reward_sum", "progress_sum", "reset_count")},
     }
+    if rank_ms is not None:
+        line["rank_ms_per_step"] = rank_ms
     if rank == 0 and not args.no_extras and variant != "base":
         # the learner side of the path, context only
         try:
