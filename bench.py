@@ -348,9 +348,11 @@ def time_steps(tasks, steps, warmup, with_pre, log_every, world, dist):
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     folds = sum(1 for i in range(steps) if is_log(i))
     eager = world > 1 and not in_graph_collective and folds > 0
-    # keep the GPU busy (~100 us) while the host enqueues the start event and the first graph launch: the timed region
-    # then holds device time of the K steps, not the host's cudaGraphLaunch latency (8 us against 300 us at --steps 20)
-    torch.cuda._sleep(200000)
+    # keep the GPU busy (~1 ms) while the host enqueues the start event and the first graph launch: the timed region
+    # then holds device time of the K steps, not the host's cudaGraphLaunch latency (8 us against 300 us at --steps 20;
+    # occasionally far more when the launch waits for the driver lock behind an NVML query of the clock sampler, which
+    # showed as a +3..10 % outlier of one rank in one of three runs with a 100-us sleep)
+    torch.cuda._sleep(2000000)
     if world > 1:
         # device-side start line: the ranks' streams leave this tiny all-reduce together, so the timed region of a
         # rank whose host came out of the barrier early does not include waiting (inside the captured collective)
