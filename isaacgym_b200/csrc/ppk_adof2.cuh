@@ -104,15 +104,15 @@ adof2_step_kernel(const __grid_constant__ KArgs k) {
 #pragma unroll
       for (int e = 0; e < T; ++e) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(g_rb + (size_t)e * L::kRbEnv + root_id * kRow) & ~(uintptr_t)15;
-        bulk_g2s(row0_s + e * 16, reinterpret_cast<const void*>(a), 64u, bar);
+        bulk_g2s_in(row0_s + e * 16, reinterpret_cast<const void*>(a), 64u, bar);
       }
       mbar_arrive_expect_tx(bar + 1, L::kTx);
-      bulk_g2s(rb_s, g_rb, 4u * T * L::kRbEnv, bar + 1);
-      bulk_g2s(init_s, k.init_bal + (size_t)env0 * L::kInitEnv, 4u * T * L::kInitEnv, bar + 1);
-      bulk_g2s(root_s, k.root + (size_t)env0 * L::kRoot, 4u * T * L::kRoot, bar + 1);
-      bulk_g2s(dof_s, k.dof + (size_t)env0 * L::kDof, 4u * T * L::kDof, bar + 1);
-      bulk_g2s(idof_s, k.init_dof + (size_t)env0 * L::kDof, 4u * T * L::kDof, bar + 1);
-      bulk_g2s(force_s, k.force + (size_t)env0 * D, 4u * T * D, bar + 1);
+      bulk_g2s_in(rb_s, g_rb, 4u * T * L::kRbEnv, bar + 1);
+      bulk_g2s_in(init_s, k.init_bal + (size_t)env0 * L::kInitEnv, 4u * T * L::kInitEnv, bar + 1);
+      bulk_g2s_in(root_s, k.root + (size_t)env0 * L::kRoot, 4u * T * L::kRoot, bar + 1);
+      bulk_g2s_in(dof_s, k.dof + (size_t)env0 * L::kDof, 4u * T * L::kDof, bar + 1);
+      bulk_g2s_in(idof_s, k.init_dof + (size_t)env0 * L::kDof, 4u * T * L::kDof, bar + 1);
+      bulk_g2s_in(force_s, k.force + (size_t)env0 * D, 4u * T * D, bar + 1);
     }
     __syncwarp();
   }
@@ -507,7 +507,7 @@ adof2_step_kernel(const __grid_constant__ KArgs k) {
   fence_proxy_async();
   __syncthreads();
   if (threadIdx.x == 0) {
-    bulk_s2g(k.obs + (size_t)env0 * kAdofObs, obs_s, 4u * T * kAdofObs);
+    bulk_s2g_out(k.obs + (size_t)env0 * kAdofObs, obs_s, 4u * T * kAdofObs);
     bulk_commit();
     bulk_wait_read();
   }

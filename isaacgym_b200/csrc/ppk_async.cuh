@@ -118,6 +118,42 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
                : "memory");
 }
+// ---- the step kernels' streams with an L2 eviction-priority hint (A/B builds: -DPPK_L2_HINT=1 loads, 2 stores, 3 both):
+// every input byte is read once and every output byte is written once per step, so evict-first would be the natural
+// policy.  Measured (profiles/r2_l2_hint.log): on the loads it COSTS 4-7 % (TILT 65 536 envs 14.7 -> 15.7 us, 1 M envs
+// 187 -> 195 us, ADOF 28.3 -> 29.4 us), on the stores it changes nothing: the default stays without a hint
+#ifndef PPK_L2_HINT
+#define PPK_L2_HINT 0
+#endif
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_in(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  if (PPK_L2_HINT & 1)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(l2_evict_first_policy())
+                 : "memory");
+  else bulk_g2s(dst_smem, src_gmem, bytes, bar);
+}
+__device__ __forceinline__ void tma_load_2d_in(void* dst_smem, const void* tensor_map, int c0, int c1, uint64_t* bar) {
+  if (PPK_L2_HINT & 1)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(l2_evict_first_policy())
+        : "memory");
+  else tma_load_2d(dst_smem, tensor_map, c0, c1, bar);
+}
+__device__ __forceinline__ void bulk_s2g_out(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  if (PPK_L2_HINT & 2)
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes), "l"(l2_evict_first_policy())
+                 : "memory");
+  else bulk_s2g(dst_gmem, src_smem, bytes);
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the issuing thread may not exit (shared memory is released) before the source has been read
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

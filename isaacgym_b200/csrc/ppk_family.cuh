@@ -142,16 +142,16 @@ family_step_kernel(const __grid_constant__ KArgs k, const __grid_constant__ CUte
 #pragma unroll
         for (int h = 0; h < H; ++h)
 #pragma unroll
-          for (int q = 0; q < 2; ++q) tma_load_2d(row0_s + (h * 2 + q) * L::kPairs * r0s, &m_row0, k.row0_c[h][q], p0, bar);
+          for (int q = 0; q < 2; ++q) tma_load_2d_in(row0_s + (h * 2 + q) * L::kPairs * r0s, &m_row0, k.row0_c[h][q], p0, bar);
         mbar_arrive_expect_tx(bar + 1, 4u * L::kUnits * L::kSpanF + L::kLinearTx);
-        bulk_g2s(root_s, k.root + (size_t)env0 * L::kRootEnv, 4u * TILE * L::kRootEnv, bar + 1);
-        bulk_g2s(dof_s, k.dof + (size_t)env0 * 2 * D, 4u * TILE * 2 * D, bar + 1);
-        bulk_g2s(force_s, k.force + (size_t)env0 * D, 4u * TILE * D, bar + 1);
+        bulk_g2s_in(root_s, k.root + (size_t)env0 * L::kRootEnv, 4u * TILE * L::kRootEnv, bar + 1);
+        bulk_g2s_in(dof_s, k.dof + (size_t)env0 * 2 * D, 4u * TILE * 2 * D, bar + 1);
+        bulk_g2s_in(force_s, k.force + (size_t)env0 * D, 4u * TILE * D, bar + 1);
 #pragma unroll
         for (int h = 0; h < H; ++h)
 #pragma unroll
           for (int q = 0; q < 2; ++q)
-            tma_load_2d(span_s + (h * 2 + q) * L::kPairs * L::kSpanF, &m_span, k.span_c[h][q], p0, bar + 1);
+            tma_load_2d_in(span_s + (h * 2 + q) * L::kPairs * L::kSpanF, &m_span, k.span_c[h][q], p0, bar + 1);
       }
       __syncwarp();
     }
@@ -523,7 +523,7 @@ family_step_kernel(const __grid_constant__ KArgs k, const __grid_constant__ CUte
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
-      bulk_s2g(g_obs, obs_s, 4u * L::kUnits * L::kObs);
+      bulk_s2g_out(g_obs, obs_s, 4u * L::kUnits * L::kObs);
       bulk_commit();
     }
   } else {
