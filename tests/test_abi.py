@@ -124,6 +124,18 @@ def test_learner_side_argument_validation(lib):
     assert lib.ppk_policy_first_layer(None, 0x1000, 16, 80, 0x1000, 2048, 7, 0x1000, None) == -4   # activation
     assert lib.ppk_policy_first_layer(None, None, 16, 80, 0x1000, 2048, 1, 0x1000, None) == -1
     assert lib.ppk_policy_first_layer(None, 0x1000, 0, 80, 0x1000, 2048, 1, 0x1000, None) == 0     # empty batch
+    # fp32 (rollout-forward) variant: 8 bytes per packed element (TF32 hi + lo), K padded to a multiple of 8 with the bias column
+    assert lib.ppk_linear_packed_bytes_f32(2048, 80) == 2048 * 88 * 8
+    assert lib.ppk_linear_packed_bytes_f32(2048, 94) == 2048 * 96 * 8
+    assert lib.ppk_linear_packed_bytes_f32(256, 24) == 256 * 32 * 8
+    assert lib.ppk_linear_packed_bytes_f32(1000, 80) == 0
+    assert lib.ppk_linear_pack_f32(None, None, 256, 80, 0x1000, 1 << 20, None) == -1
+    assert lib.ppk_linear_pack_f32(0x1000, None, 256, 80, 0x1000, 16, None) == -2                  # packed buffer too small
+    assert lib.ppk_policy_first_layer_f32(None, 0x1000, 16, 80, 0x1000, 1000, 1, 0x1000, None) == -2   # units
+    assert lib.ppk_policy_first_layer_f32(None, 0x1000, 16, 80, 0x1000, 2048, 7, 0x1000, None) == -4   # activation
+    assert lib.ppk_policy_first_layer_f32(None, None, 16, 80, 0x1000, 2048, 1, 0x1000, None) == -1
+    assert lib.ppk_policy_first_layer_f32(None, 0x1000, 16, 80, 0x1004, 2048, 1, 0x1000, None) == -3   # packed weights not 16-byte aligned
+    assert lib.ppk_policy_first_layer_f32(None, 0x1000, 0, 80, 0x1000, 2048, 1, 0x1000, None) == 0     # empty batch
 
 
 def test_learner_side_host_mirror_is_cuda_only():
