@@ -420,11 +420,16 @@ int ppk_sample_ball_launch(const PpkTask* t, const PpkBuffers* b, uint64_t seed,
   if (!b->reset_ball_vel || (t->variant == PPK_ADOF && !b->reset_ball_pos_yz)) return PPK_ERR_NULL;
   if (refresh_consumed_only && !b->reset_buf) return PPK_ERR_NULL;
   const long long blocks = (b->num_envs + 255) / 256;
-  sample_launch_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      const_cast<float*>(b->reset_ball_vel), const_cast<float*>(b->reset_ball_pos_yz),
-      refresh_consumed_only ? reinterpret_cast<const long long*>(b->reset_buf) : nullptr, b->num_envs, t->variant,
-      (unsigned long long)seed, (unsigned long long)epoch, (long long)env_offset);
-  return cudaGetLastError() == cudaSuccess ? PPK_OK : PPK_ERR_LAUNCH;
+  // a programmatic dependent of the step kernel it usually follows: resident when that grid retires (it waits for it
+  // before its first access: the step reads the rows this kernel rewrites)
+  if (launch_pdl(sample_launch_kernel, (unsigned)blocks, 256u, 0, static_cast<cudaStream_t>(stream),
+                 const_cast<float*>(b->reset_ball_vel), const_cast<float*>(b->reset_ball_pos_yz),
+                 refresh_consumed_only ? reinterpret_cast<const long long*>(b->reset_buf) : nullptr, (long long)b->num_envs,
+                 (int)t->variant, (unsigned long long)seed, (unsigned long long)epoch, (long long)env_offset) != cudaSuccess) {
+    cudaGetLastError();
+    return PPK_ERR_LAUNCH;
+  }
+  return PPK_OK;
 }
 
 // Used by the host session: the shard-wide ADOF counter clear after all chunks ran (ADOF:1162-1175).

@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(256)
 sample_launch_kernel(float* __restrict__ vel, float* __restrict__ pos_yz, const long long* __restrict__ only_if_reset,
                      long long n, int variant, unsigned long long seed, unsigned long long epoch, long long env_offset) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  gdc_wait();                                                         // the step kernel ahead reads these rows and writes reset_buf
   if (e >= n) return;
   if (only_if_reset != nullptr && only_if_reset[e] == 0) return;      // refresh only the rows just consumed
   const unsigned long long g = (unsigned long long)(e + env_offset);  // global env id: shards draw disjoint streams
